@@ -1,0 +1,133 @@
+// Internal declarations shared by the translation units of libweather_b200.so.
+// Nothing here is part of the C-ABI (include/weather_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "weather_b200.h"
+
+namespace wsb {
+
+// Ghost rows kept above and below every field so that a row slab can hold its neighbours' rows:
+// 1 per RK stage, 4 for a whole fused RK4 step.
+constexpr int kHaloRows = 4;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_last_error(const std::string &msg);
+int fail(int status, const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define WSB_CUDA(call)                                                            \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::wsb::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define WSB_TRY(call)                \
+    do {                             \
+        int _s = (call);             \
+        if (_s != WSB_OK) return _s; \
+    } while (0)
+
+// ---- device-side view of a set of (u, v, h) planes -------------------------------------------
+// All planes of a grid share one geometry: `pitch` elements per row, (rows + 2*kHaloRows) rows per
+// level, pointer at (level 0, local row 0, x 0).
+template <typename T>
+struct Planes3 {
+    T *u;
+    T *v;
+    T *h;
+};
+
+template <typename T>
+struct Geometry {
+    int W;                   // cells per row
+    int H;                   // local rows (this rank)
+    int L;                   // levels
+    int pitch;               // elements between consecutive rows
+    long long level_stride;  // elements between consecutive levels
+    int row0;                // global index of local row 0
+    int Hglobal;             // global rows (clamp boundary applies at 0 and Hglobal-1 only)
+};
+
+// Constants of one tendency evaluation (weather_simulation.cpp:486-489).
+template <typename T>
+struct Physics {
+    T ddx, ddy;    // 2.0f*dx, 2.0f*dy                         (used when !recip)
+    T rdx, rdy;    // exact reciprocals when both are powers of two (recip)
+    T g, f;
+    int recip;     // 1: (a-b)*rdx is bit-identical to (a-b)/ddx for every input
+};
+
+// One fused RK stage: k = tend(S); then either
+//   UPDATE: O = Y + c*k              (optionally also store k into KS)
+//   FINAL : O = Y + dt6*(((K1 + 2*KA) + 2*KB) + k)   with K1 := k when k1 planes are null
+// (weather_simulation.cpp:186-198, 248-260, 380-451).
+template <typename T>
+struct StageArgs {
+    Planes3<const T> S;   // stencil input state
+    Planes3<const T> Y;   // base state y_n
+    Planes3<T> O;         // output state
+    Planes3<T> KS;        // where to store k (null = don't)
+    Planes3<const T> KA;  // k2 (FINAL)
+    Planes3<const T> KB;  // k3 (FINAL)
+    Planes3<const T> K1;  // k1 (FINAL, classical mode only; null = reference aliasing, K1 := k4)
+    T c;                  // stage coefficient, already rounded: dt or (0.5f*dt)
+    T dt6;                // dt/6.0f
+    int final_stage;
+    int y_begin, y_end;   // local row range this launch covers
+};
+
+// Whole-step fused kernel arguments (all RK stages in one pass over the grid).
+template <typename T>
+struct StepArgs {
+    Planes3<const T> Y;   // y_n
+    Planes3<T> O;         // y_{n+1}
+    T dt, half_dt, dt6;
+    int classical;
+    int y_begin, y_end;   // local OUTPUT row range this launch covers
+};
+
+// ---- kernel launchers (wsb_kernels.cu) -------------------------------------------------------
+template <typename T>
+cudaError_t launch_stage_direct(const Geometry<T> &g, const Physics<T> &ph, const StageArgs<T> &a, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_diagnostics(const Geometry<T> &g, const Physics<T> &ph, const T *u, const T *v, T *vort,
+                               T *div, cudaStream_t st);
+
+// O = Y + c*k for a constant k (the Primitive-equations T/p "tendencies", weather_simulation.cpp:201-214)
+template <typename T>
+cudaError_t launch_axpy_const(const Geometry<T> &g, const T *y, T *o, T c, T k, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st);
+
+// per-block partial sums of mass and energy in double; partial[2*b], partial[2*b+1]
+template <typename T>
+cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, const T *h, double gravity,
+                               double *partial, int nblocks, cudaStream_t st);
+
+// whole-step fused path (wsb_step_fused.cu). NSTAGES in {1, 2, 4}.
+template <typename T>
+cudaError_t launch_step_fused(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
+                              cudaStream_t st);
+bool step_fused_supported(int nstages, int dtype);
+
+// ---- NCCL, loaded lazily with dlopen (wsb_nccl.cpp) -------------------------------------------
+struct NcclApi;
+int nccl_load(const NcclApi **api);
+int nccl_get_unique_id(void *out128);
+struct HaloComm;  // opaque: communicator + neighbour ranks
+int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out);
+void halo_comm_destroy(HaloComm *c);
+// Exchange `nrows` boundary rows of each of the `nplanes` planes with the up/down neighbours:
+// sends local rows [0,nrows) up and [H-nrows,H) down; receives into ghost rows [-nrows,0) and [H,H+nrows).
+int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_size, int pitch, int H, int nrows,
+                  cudaStream_t st);
+
+}  // namespace wsb

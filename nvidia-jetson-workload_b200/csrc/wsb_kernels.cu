@@ -1,0 +1,200 @@
+// Per-stage kernels and small utility kernels of libweather_b200.so (sm_100a).
+//
+// stage_direct_kernel: one RK stage fused into one pass -- tendency (the 5-point clamped stencil of
+// weather_simulation.cpp:473-540) + stage update (:186-198 / :248-260 / :380-451) -- one cell per
+// thread, coalesced direct global loads; vertical/horizontal neighbour re-reads are served by L1/L2.
+// It is the simplest correct path and the A/B baseline for the TMA-tiled and whole-step fused variants.
+#include "wsb_arith.cuh"
+#include "wsb_internal.h"
+
+namespace wsb {
+
+namespace {
+
+constexpr int kBX = 64;
+constexpr int kBY = 4;
+
+template <typename T, bool RECIP, bool FINAL, bool STORE_K>
+__global__ void __launch_bounds__(kBX *kBY)
+    stage_direct_kernel(const Geometry<T> g, const Physics<T> ph, const StageArgs<T> a) {
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = a.y_begin + blockIdx.y * kBY + threadIdx.y;
+    if (x >= g.W || y >= a.y_end) return;
+    const long long base = (long long)blockIdx.z * g.level_stride;
+    const long long i = base + (long long)y * g.pitch + x;
+    const int gy = g.row0 + y;
+    // clamp-to-self neighbours (weather_simulation.cpp:510-513); slab edges read ghost rows
+    const long long iL = (x > 0) ? i - 1 : i;
+    const long long iR = (x < g.W - 1) ? i + 1 : i;
+    const long long iU = (gy > 0) ? i - g.pitch : i;
+    const long long iD = (gy < g.Hglobal - 1) ? i + g.pitch : i;
+
+    const T u = a.S.u[i], v = a.S.v[i], h = a.S.h[i];
+    T du, dv, dh;
+    tendency_cell<T, RECIP>(ph, u, v, h, a.S.u[iL], a.S.u[iR], a.S.u[iU], a.S.u[iD], a.S.v[iL], a.S.v[iR], a.S.v[iU],
+                            a.S.v[iD], a.S.h[iL], a.S.h[iR], a.S.h[iU], a.S.h[iD], du, dv, dh);
+    if (STORE_K) {
+        a.KS.u[i] = du;
+        a.KS.v[i] = dv;
+        a.KS.h[i] = dh;
+    }
+    const T yu = a.Y.u[i], yv = a.Y.v[i], yh = a.Y.h[i];
+    if (FINAL) {
+        const T k1u = a.K1.u ? a.K1.u[i] : du;
+        const T k1v = a.K1.v ? a.K1.v[i] : dv;
+        const T k1h = a.K1.h ? a.K1.h[i] : dh;
+        a.O.u[i] = rk4_combine<T>(yu, a.dt6, k1u, a.KA.u[i], a.KB.u[i], du);
+        a.O.v[i] = rk4_combine<T>(yv, a.dt6, k1v, a.KA.v[i], a.KB.v[i], dv);
+        a.O.h[i] = rk4_combine<T>(yh, a.dt6, k1h, a.KA.h[i], a.KB.h[i], dh);
+    } else {
+        a.O.u[i] = axpy<T>(yu, a.c, du);
+        a.O.v[i] = axpy<T>(yv, a.c, dv);
+        a.O.h[i] = axpy<T>(yh, a.c, dh);
+    }
+}
+
+template <typename T, bool RECIP>
+__global__ void __launch_bounds__(kBX *kBY)
+    diagnostics_kernel(const Geometry<T> g, const Physics<T> ph, const T *__restrict__ u, const T *__restrict__ v,
+                       T *__restrict__ vort, T *__restrict__ dvg) {
+    using A = Ar<T>;
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const long long i = (long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x;
+    const int gy = g.row0 + y;
+    const long long iL = (x > 0) ? i - 1 : i;
+    const long long iR = (x < g.W - 1) ? i + 1 : i;
+    const long long iU = (gy > 0) ? i - g.pitch : i;
+    const long long iD = (gy < g.Hglobal - 1) ? i + g.pitch : i;
+    // weather_grid.cpp:96-100 and :114-118
+    const T dv_dx = cdiff<T, RECIP>(v[iR], v[iL], ph.ddx, ph.rdx);
+    const T du_dy = cdiff<T, RECIP>(u[iD], u[iU], ph.ddy, ph.rdy);
+    const T du_dx = cdiff<T, RECIP>(u[iR], u[iL], ph.ddx, ph.rdx);
+    const T dv_dy = cdiff<T, RECIP>(v[iD], v[iU], ph.ddy, ph.rdy);
+    vort[i] = A::sub(dv_dx, du_dy);
+    dvg[i] = A::add(du_dx, dv_dy);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBX *kBY)
+    axpy_const_kernel(const Geometry<T> g, const T *__restrict__ yv, T *__restrict__ o, T c, T k) {
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const long long i = (long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x;
+    o[i] = axpy<T>(yv[i], c, k);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBX *kBY) fill_kernel(const Geometry<T> g, T *__restrict__ p, T value, int halo) {
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = blockIdx.y * kBY + threadIdx.y - halo;
+    if (x >= g.pitch || y >= g.H + halo) return;
+    p[(long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x] = value;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    mass_energy_kernel(const Geometry<T> g, const T *__restrict__ u, const T *__restrict__ v, const T *__restrict__ h,
+                       double gravity, double *__restrict__ partial) {
+    double m = 0.0, e = 0.0;
+    const long long cells_per_level = (long long)g.W * g.H;
+    const long long total = cells_per_level * g.L;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+         c += (long long)gridDim.x * blockDim.x) {
+        const long long lvl = c / cells_per_level;
+        const long long r = c - lvl * cells_per_level;
+        const long long y = r / g.W, x = r - y * g.W;
+        const long long i = lvl * g.level_stride + y * g.pitch + x;
+        const double hu = (double)u[i], hv = (double)v[i], hh = (double)h[i];
+        m += hh;
+        e += 0.5 * hh * (hu * hu + hv * hv) + 0.5 * gravity * hh * hh;
+    }
+    __shared__ double sm[256], se[256];
+    sm[threadIdx.x] = m;
+    se[threadIdx.x] = e;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            sm[threadIdx.x] += sm[threadIdx.x + s];
+            se[threadIdx.x] += se[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = sm[0];
+        partial[2 * blockIdx.x + 1] = se[0];
+    }
+}
+
+template <typename T>
+dim3 grid_for(const Geometry<T> &g, int rows, int cols) {
+    return dim3((cols + kBX - 1) / kBX, (rows + kBY - 1) / kBY, g.L);
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t launch_stage_direct(const Geometry<T> &g, const Physics<T> &ph, const StageArgs<T> &a, cudaStream_t st) {
+    const int rows = a.y_end - a.y_begin;
+    if (rows <= 0) return cudaSuccess;
+    const dim3 grid = grid_for(g, rows, g.W), block(kBX, kBY);
+    const bool store = a.KS.u != nullptr;
+#define WSB_LAUNCH(R, F, S) stage_direct_kernel<T, R, F, S><<<grid, block, 0, st>>>(g, ph, a)
+    if (ph.recip) {
+        if (a.final_stage) WSB_LAUNCH(true, true, false);
+        else if (store) WSB_LAUNCH(true, false, true);
+        else WSB_LAUNCH(true, false, false);
+    } else {
+        if (a.final_stage) WSB_LAUNCH(false, true, false);
+        else if (store) WSB_LAUNCH(false, false, true);
+        else WSB_LAUNCH(false, false, false);
+    }
+#undef WSB_LAUNCH
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_diagnostics(const Geometry<T> &g, const Physics<T> &ph, const T *u, const T *v, T *vort, T *dvg,
+                               cudaStream_t st) {
+    const dim3 grid = grid_for(g, g.H, g.W), block(kBX, kBY);
+    if (ph.recip) diagnostics_kernel<T, true><<<grid, block, 0, st>>>(g, ph, u, v, vort, dvg);
+    else diagnostics_kernel<T, false><<<grid, block, 0, st>>>(g, ph, u, v, vort, dvg);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_axpy_const(const Geometry<T> &g, const T *y, T *o, T c, T k, cudaStream_t st) {
+    axpy_const_kernel<T><<<grid_for(g, g.H, g.W), dim3(kBX, kBY), 0, st>>>(g, y, o, c, k);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st) {
+    const int halo = with_halo ? kHaloRows : 0;
+    fill_kernel<T><<<grid_for(g, g.H + 2 * halo, g.pitch), dim3(kBX, kBY), 0, st>>>(g, p, value, halo);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, const T *h, double gravity,
+                               double *partial, int nblocks, cudaStream_t st) {
+    mass_energy_kernel<T><<<nblocks, 256, 0, st>>>(g, u, v, h, gravity, partial);
+    return cudaGetLastError();
+}
+
+#define WSB_INSTANTIATE(T)                                                                                          \
+    template cudaError_t launch_stage_direct<T>(const Geometry<T> &, const Physics<T> &, const StageArgs<T> &,       \
+                                                cudaStream_t);                                                      \
+    template cudaError_t launch_diagnostics<T>(const Geometry<T> &, const Physics<T> &, const T *, const T *, T *,   \
+                                               T *, cudaStream_t);                                                  \
+    template cudaError_t launch_axpy_const<T>(const Geometry<T> &, const T *, T *, T, T, cudaStream_t);              \
+    template cudaError_t launch_fill<T>(const Geometry<T> &, T *, T, bool, cudaStream_t);                            \
+    template cudaError_t launch_mass_energy<T>(const Geometry<T> &, const T *, const T *, const T *, double,         \
+                                               double *, int, cudaStream_t);
+WSB_INSTANTIATE(float)
+WSB_INSTANTIATE(double)
+#undef WSB_INSTANTIATE
+
+}  // namespace wsb

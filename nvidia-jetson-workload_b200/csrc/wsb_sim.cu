@@ -1,0 +1,1032 @@
+// Host side of libweather_b200.so: device-resident WeatherGrid / WeatherSimulation behind the C-ABI
+// of include/weather_b200.h. Mirrors the reference's driver (weather_simulation.cpp:17-158) and grid
+// (weather_grid.cpp:15-142), with the arithmetic in hand-written sm_100a kernels.
+//
+// There is NO CPU compute path in this file: every field lives in HBM and every update is a kernel.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "wsb_internal.h"
+
+namespace wsb {
+
+// ------------------------------------------------------------------------------------ errors --
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+int fail(int status, const std::string &msg) {
+    g_last_error = msg;
+    return status;
+}
+
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line) {
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(err) + " in " + what + " (" + file + ":" +
+                   std::to_string(line) + ")";
+    // leave the sticky error readable for the caller but clear the "last error" slot
+    cudaGetLastError();
+    return err == cudaErrorMemoryAllocation ? WSB_ERR_OUT_OF_MEMORY : WSB_ERR_CUDA;
+}
+
+static inline size_t elem_size(int dtype) { return dtype == WSB_F64 ? sizeof(double) : sizeof(float); }
+
+// reset() defaults, weather_grid.cpp:57-71. The float literals are the reference's; for WSB_F64 they are
+// the same float values widened (what `std::fill(..., 288.15f)` would store in a vector<double>).
+static const float kResetValue[WSB_NUM_FIELDS] = {0.0f, 0.0f, 10.0f, 1013.25f, 288.15f, 0.0f, 0.0f, 0.0f};
+
+static bool is_pow2(double x) {
+    if (!(x > 0) || !std::isfinite(x)) return false;
+    int e;
+    return std::frexp(x, &e) == 0.5;
+}
+
+}  // namespace wsb
+
+using namespace wsb;
+
+// -------------------------------------------------------------------------------------- grid --
+// One plane set of a field: lazily allocated. While `ptr == nullptr` the field is uniformly `uniform`
+// (e.g. p/T/q of a shallow-water run are never touched: they cost no HBM).
+struct FieldBuf {
+    void *base = nullptr;  // allocation start (includes ghost rows)
+    double uniform = 0.0;
+};
+
+struct wsb_grid {
+    int W = 0, H = 0, L = 1;     // local extent
+    int dtype = WSB_F32;
+    int device = 0;
+    double dx = 1.0, dy = 1.0;   // already rounded to the grid dtype
+    int pitch = 0;               // elements
+    long long level_stride = 0;  // elements
+    int row0 = 0, Hglobal = 0;   // slab position (standalone grid: 0, H)
+    FieldBuf f[WSB_NUM_FIELDS];
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    wsb_sim *owner = nullptr;    // non-null for a simulation's current grid
+    double transfer_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    size_t plane_bytes() const { return (size_t)L * (size_t)level_stride * elem_size(dtype); }
+    // pointer to (level 0, local row 0, x 0)
+    void *origin(int field) const {
+        if (!f[field].base) return nullptr;
+        return (char *)f[field].base + (size_t)kHaloRows * pitch * elem_size(dtype);
+    }
+    template <typename T>
+    Geometry<T> geom() const {
+        Geometry<T> g;
+        g.W = W; g.H = H; g.L = L; g.pitch = pitch; g.level_stride = level_stride; g.row0 = row0; g.Hglobal = Hglobal;
+        return g;
+    }
+    template <typename T>
+    Physics<T> physics(double gravity, double coriolis) const {
+        Physics<T> p;
+        const T tdx = (T)dx, tdy = (T)dy;
+        p.ddx = T(2.0f) * tdx;  // `2.0f * dx` (weather_simulation.cpp:521): exact in both types
+        p.ddy = T(2.0f) * tdy;
+        p.recip = is_pow2((double)p.ddx) && is_pow2((double)p.ddy);
+        p.rdx = p.recip ? T(1) / p.ddx : T(0);
+        p.rdy = p.recip ? T(1) / p.ddy : T(0);
+        p.g = (T)gravity;
+        p.f = (T)coriolis;
+        return p;
+    }
+};
+
+static int grid_alloc_plane(wsb_grid *g, void **out) {
+    WSB_CUDA(cudaSetDevice(g->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, g->plane_bytes());
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(field plane)", __FILE__, __LINE__);
+    *out = p;
+    return WSB_OK;
+}
+
+static int grid_fill(wsb_grid *g, void *base, double value) {
+    void *origin = (char *)base + (size_t)kHaloRows * g->pitch * elem_size(g->dtype);
+    if (g->dtype == WSB_F64) WSB_CUDA(launch_fill<double>(g->geom<double>(), (double *)origin, value, true, g->stream));
+    else WSB_CUDA(launch_fill<float>(g->geom<float>(), (float *)origin, (float)value, true, g->stream));
+    return WSB_OK;
+}
+
+// make sure the field has device storage (materialising its uniform value)
+static int grid_materialize(wsb_grid *g, int field) {
+    if (g->f[field].base) return WSB_OK;
+    void *p = nullptr;
+    WSB_TRY(grid_alloc_plane(g, &p));
+    g->f[field].base = p;
+    return grid_fill(g, p, g->f[field].uniform);
+}
+
+static void grid_release(wsb_grid *g, int field, double uniform) {
+    if (g->f[field].base) {
+        cudaFree(g->f[field].base);
+        g->f[field].base = nullptr;
+    }
+    g->f[field].uniform = uniform;
+}
+
+static int grid_init(wsb_grid *g, int W, int H, int L, double dx, double dy, int dtype, int device, int row0,
+                     int Hglobal, cudaStream_t stream) {
+    if (W <= 0 || H <= 0 || L <= 0)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "Grid dimensions must be positive");  // weather_grid.cpp:29-31
+    if (dtype != WSB_F32 && dtype != WSB_F64) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown dtype");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(WSB_ERR_CUDA, "no CUDA device available: libweather_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(WSB_ERR_INVALID_ARGUMENT, "device_id out of range");
+    g->W = W; g->H = H; g->L = L; g->dtype = dtype; g->device = device;
+    g->dx = dtype == WSB_F32 ? (double)(float)dx : dx;
+    g->dy = dtype == WSB_F32 ? (double)(float)dy : dy;
+    const int align = 128 / (int)elem_size(dtype);  // rows start on 128-byte boundaries
+    g->pitch = (W + align - 1) / align * align;
+    g->level_stride = (long long)(H + 2 * kHaloRows) * g->pitch;
+    g->row0 = row0;
+    g->Hglobal = Hglobal;
+    WSB_CUDA(cudaSetDevice(device));
+    if (stream) {
+        g->stream = stream;
+    } else {
+        WSB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        g->owns_stream = true;
+    }
+    WSB_CUDA(cudaEventCreate(&g->ev0));
+    WSB_CUDA(cudaEventCreate(&g->ev1));
+    for (int k = 0; k < WSB_NUM_FIELDS; ++k) g->f[k].uniform = (double)kResetValue[k];
+    // u, v, h always live on the device; the rest are materialised on first touch
+    for (int k = 0; k <= WSB_FIELD_HEIGHT; ++k) WSB_TRY(grid_materialize(g, k));
+    return WSB_OK;
+}
+
+static void grid_fini(wsb_grid *g) {
+    cudaSetDevice(g->device);
+    for (int k = 0; k < WSB_NUM_FIELDS; ++k)
+        if (g->f[k].base) cudaFree(g->f[k].base);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->owns_stream && g->stream) cudaStreamDestroy(g->stream);
+}
+
+// --------------------------------------------------------------------------------------- sim --
+enum KernelPath { PATH_STAGE_DIRECT = 1, PATH_STAGE_TMA = 2, PATH_STEP_FUSED = 3 };
+
+struct wsb_sim {
+    wsb_config cfg{};
+    int dtype = WSB_F32;
+    double dt = 0.01;         // rounded to dtype
+    double time = 0.0;        // accumulated in dtype (float add for WSB_F32, weather_sim.hpp:527)
+    int step = 0;
+    int nstages = 1;          // 1 Euler-like, 2 RK2, 4 RK4
+    int path = PATH_STAGE_DIRECT;
+    int row0 = 0, nrows = 0;
+    wsb_grid cur;             // the live "current grid" (u,v,h pointers rotate with `next`)
+    // the reference swaps whole grids (weather_simulation.cpp:217): p/T/q of the "next" grid become current
+    FieldBuf alt[WSB_NUM_FIELDS];
+    void *next[3] = {nullptr, nullptr, nullptr};   // y_{n+1} planes
+    void *tA[3] = {nullptr, nullptr, nullptr};     // stage scratch (per-stage paths)
+    void *tB[3] = {nullptr, nullptr, nullptr};
+    void *k1[3] = {nullptr, nullptr, nullptr};
+    void *k2[3] = {nullptr, nullptr, nullptr};
+    void *k3[3] = {nullptr, nullptr, nullptr};
+    bool diag_dirty = false;  // vorticity/divergence need recomputing from the current u, v
+    bool halo_valid = false;  // ghost rows of the current state are up to date (nranks > 1)
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
+    bool run_open = false;    // ev_start recorded, ev_stop pending
+    double last_run_ms = 0.0;
+    wsb_metrics metrics{};
+    HaloComm *comm = nullptr;
+    double *d_partial = nullptr;
+    int npartial = 0;
+};
+
+static void *plane_origin(const wsb_sim *s, void *base) {
+    return base ? (char *)base + (size_t)kHaloRows * s->cur.pitch * elem_size(s->dtype) : nullptr;
+}
+
+static int sim_alloc3(wsb_sim *s, void *dst[3]) {
+    for (int k = 0; k < 3; ++k) WSB_TRY(grid_alloc_plane(&s->cur, &dst[k]));
+    return WSB_OK;
+}
+
+static void sim_free3(void *p[3]) {
+    for (int k = 0; k < 3; ++k) {
+        if (p[k]) cudaFree(p[k]);
+        p[k] = nullptr;
+    }
+}
+
+template <typename T>
+static Planes3<T> planes(const wsb_sim *s, void *const p[3]) {
+    Planes3<T> r;
+    r.u = (T *)plane_origin(s, p[0]);
+    r.v = (T *)plane_origin(s, p[1]);
+    r.h = (T *)plane_origin(s, p[2]);
+    return r;
+}
+
+template <typename T>
+static Planes3<T> null_planes() {
+    Planes3<T> r;
+    r.u = r.v = r.h = nullptr;
+    return r;
+}
+
+static int effective_stages(const wsb_config &c) {
+    switch (c.integration_method) {
+        case WSB_INT_RUNGE_KUTTA_2: return 2;
+        case WSB_INT_RUNGE_KUTTA_4:
+            return c.model == WSB_MODEL_SHALLOW_WATER ? 4 : 2;  // weather_simulation.cpp:334-338
+        default: return 1;  // Euler, AdamsBashforth, SemiImplicit (:457-471)
+    }
+}
+
+// ghost-row exchange of 3 planes on the comm stream, ordered after `after` and signalling ev_halo
+static int sim_exchange(wsb_sim *s, void *const p[3], int nrows_halo, cudaEvent_t after) {
+    if (!s->comm) return WSB_OK;
+    WSB_CUDA(cudaStreamWaitEvent(s->comm_stream, after, 0));
+    WSB_CUDA(cudaEventRecord(s->ev_h0, s->comm_stream));
+    void *origins[3] = {plane_origin(s, p[0]), plane_origin(s, p[1]), plane_origin(s, p[2])};
+    WSB_TRY(halo_exchange(s->comm, origins, 3, elem_size(s->dtype), s->cur.pitch, s->cur.H, nrows_halo,
+                          s->comm_stream));
+    WSB_CUDA(cudaEventRecord(s->ev_h1, s->comm_stream));
+    WSB_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+    return WSB_OK;
+}
+
+// Enqueue one fused RK stage. With a decomposition the edge rows go first so that their exchange
+// overlaps the interior launch.
+template <typename T>
+static int enqueue_stage(wsb_sim *s, StageArgs<T> a, void *const out_planes[3], bool exchange_output) {
+    const Geometry<T> g = s->cur.geom<T>();
+    const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    const int H = s->cur.H;
+    if (!s->comm) {
+        a.y_begin = 0;
+        a.y_end = H;
+        WSB_CUDA(launch_stage_direct<T>(g, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+        return WSB_OK;
+    }
+    // input ghosts must have landed
+    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    const int e = std::min(1, H);
+    a.y_begin = 0; a.y_end = e;
+    WSB_CUDA(launch_stage_direct<T>(g, ph, a, s->stream));
+    s->metrics.kernel_launches += 1;
+    if (H > e) {
+        a.y_begin = std::max(e, H - 1); a.y_end = H;
+        WSB_CUDA(launch_stage_direct<T>(g, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+    }
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    if (exchange_output) WSB_TRY(sim_exchange(s, out_planes, 1, s->ev_edge));
+    if (H > 2) {
+        a.y_begin = 1; a.y_end = H - 1;
+        WSB_CUDA(launch_stage_direct<T>(g, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+    }
+    return WSB_OK;
+}
+
+template <typename T>
+static int enqueue_step_stages(wsb_sim *s) {
+    const T dt = (T)s->dt;
+    const T half_dt = T(0.5f) * dt;  // `0.5f * dt_` (weather_simulation.cpp:249): one rounding
+    const T dt6 = dt / T(6.0f);      // `dt_ / 6.0f` (:438)
+    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
+    const Planes3<const T> Y = planes<const T>(s, cur3);
+    StageArgs<T> a{};
+    a.Y = Y;
+    a.KS = null_planes<T>();
+    a.KA = a.KB = a.K1 = null_planes<const T>();
+    a.dt6 = dt6;
+    a.final_stage = 0;
+    if (s->nstages == 1) {  // weather_simulation.cpp:160-218
+        a.S = Y; a.O = planes<T>(s, s->next); a.c = dt;
+        WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
+    } else if (s->nstages == 2) {  // :220-323
+        a.S = Y; a.O = planes<T>(s, s->tA); a.c = half_dt;
+        WSB_TRY(enqueue_stage<T>(s, a, s->tA, true));
+        a.S = planes<const T>(s, s->tA); a.O = planes<T>(s, s->next); a.c = dt;
+        WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
+    } else {  // :325-455
+        const bool classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
+        a.S = Y; a.O = planes<T>(s, s->tA); a.c = half_dt;
+        if (classical) a.KS = planes<T>(s, s->k1);
+        WSB_TRY(enqueue_stage<T>(s, a, s->tA, true));
+        a.S = planes<const T>(s, s->tA); a.O = planes<T>(s, s->tB); a.c = half_dt; a.KS = planes<T>(s, s->k2);
+        WSB_TRY(enqueue_stage<T>(s, a, s->tB, true));
+        a.S = planes<const T>(s, s->tB); a.O = planes<T>(s, s->tA); a.c = dt; a.KS = planes<T>(s, s->k3);
+        WSB_TRY(enqueue_stage<T>(s, a, s->tA, true));
+        a.S = planes<const T>(s, s->tA); a.O = planes<T>(s, s->next); a.KS = null_planes<T>();
+        a.KA = planes<const T>(s, s->k2); a.KB = planes<const T>(s, s->k3);
+        a.K1 = classical ? planes<const T>(s, s->k1) : null_planes<const T>();
+        a.final_stage = 1;
+        WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
+    }
+    return WSB_OK;
+}
+
+template <typename T>
+static int enqueue_step_fused(wsb_sim *s) {
+    const Geometry<T> g = s->cur.geom<T>();
+    const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
+    StepArgs<T> a{};
+    a.Y = planes<const T>(s, cur3);
+    a.O = planes<T>(s, s->next);
+    a.dt = (T)s->dt;
+    a.half_dt = T(0.5f) * a.dt;
+    a.dt6 = a.dt / T(6.0f);
+    a.classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
+    const int H = s->cur.H;
+    const int halo = s->nstages;  // one ghost row per fused stage
+    if (!s->comm) {
+        a.y_begin = 0; a.y_end = H;
+        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        s->metrics.kernel_launches += 1;
+        return WSB_OK;
+    }
+    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    const int e = std::min(halo, H);
+    a.y_begin = 0; a.y_end = e;
+    WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+    s->metrics.kernel_launches += 1;
+    if (H > e) {
+        a.y_begin = std::max(e, H - halo); a.y_end = H;
+        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        s->metrics.kernel_launches += 1;
+    }
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    WSB_TRY(sim_exchange(s, s->next, halo, s->ev_edge));
+    if (H > 2 * halo) {
+        a.y_begin = halo; a.y_end = H - halo;
+        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        s->metrics.kernel_launches += 1;
+    }
+    return WSB_OK;
+}
+
+// the constant T/p drift of the PrimitiveEquations model (weather_simulation.cpp:201-214, 311-319; F7):
+// next.T = cur.T + dt*288.15f, next.p = cur.p + dt*1013.25f (the tendency grid holds its reset() values)
+template <typename T>
+static int enqueue_primitive_tp(wsb_sim *s) {
+    const Geometry<T> g = s->cur.geom<T>();
+    const int fields[2] = {WSB_FIELD_TEMPERATURE, WSB_FIELD_PRESSURE};
+    for (int k = 0; k < 2; ++k) {
+        const int fld = fields[k];
+        WSB_TRY(grid_materialize(&s->cur, fld));
+        if (!s->alt[fld].base) {
+            WSB_TRY(grid_alloc_plane(&s->cur, &s->alt[fld].base));
+        }
+        const T *y = (const T *)s->cur.origin(fld);
+        T *o = (T *)plane_origin(s, s->alt[fld].base);
+        WSB_CUDA(launch_axpy_const<T>(g, y, o, (T)s->dt, (T)kResetValue[fld], s->stream));
+        s->metrics.kernel_launches += 1;
+    }
+    return WSB_OK;
+}
+
+static int sim_ensure_halo(wsb_sim *s) {
+    if (!s->comm || s->halo_valid) return WSB_OK;
+    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    const int depth = s->path == PATH_STEP_FUSED ? s->nstages : 1;
+    WSB_TRY(sim_exchange(s, cur3, depth, s->ev_edge));
+    s->halo_valid = true;
+    return WSB_OK;
+}
+
+// one step, enqueued (weather_simulation.cpp:117-158 without the host-side bookkeeping)
+static int sim_enqueue_step(wsb_sim *s) {
+    WSB_TRY(sim_ensure_halo(s));
+    if (s->path == PATH_STEP_FUSED) {
+        if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_fused<double>(s));
+        else WSB_TRY(enqueue_step_fused<float>(s));
+    } else {
+        if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_stages<double>(s));
+        else WSB_TRY(enqueue_step_stages<float>(s));
+    }
+    if (s->cfg.model == WSB_MODEL_PRIMITIVE_EQUATIONS) {
+        if (s->dtype == WSB_F64) WSB_TRY(enqueue_primitive_tp<double>(s));
+        else WSB_TRY(enqueue_primitive_tp<float>(s));
+    }
+    // current_grid_.swap(next_grid_) (:217, :322, :454): every field of the two grids trades places
+    for (int k = 0; k < 3; ++k) std::swap(s->cur.f[k].base, s->next[k]);
+    for (int k = WSB_FIELD_PRESSURE; k <= WSB_FIELD_HUMIDITY; ++k) std::swap(s->cur.f[k], s->alt[k]);
+    s->diag_dirty = true;  // step() recomputes vorticity/divergence of the new state (:149); done lazily
+    // time and step bookkeeping in the reference's scalar type (:145-146)
+    if (s->dtype == WSB_F32) s->time = (double)((float)s->time + (float)s->dt);
+    else s->time += s->dt;
+    s->step += 1;
+    s->metrics.num_steps += 1;
+    return WSB_OK;
+}
+
+static int sim_begin_timing(wsb_sim *s) {
+    if (!s->run_open) {
+        WSB_CUDA(cudaEventRecord(s->ev_start, s->stream));
+        s->run_open = true;
+    }
+    return WSB_OK;
+}
+
+static int sim_sync(wsb_sim *s) {
+    WSB_CUDA(cudaSetDevice(s->cur.device));
+    if (s->run_open) WSB_CUDA(cudaEventRecord(s->ev_stop, s->stream));
+    if (s->comm_stream) WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
+    WSB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->run_open) {
+        float ms = 0.f;
+        WSB_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
+        s->last_run_ms = ms;
+        s->metrics.compute_time_ms += ms;
+        s->run_open = false;
+        if (s->comm) {
+            float hms = 0.f;
+            if (cudaEventElapsedTime(&hms, s->ev_h0, s->ev_h1) == cudaSuccess) s->metrics.halo_time_ms += hms;
+            else cudaGetLastError();
+        }
+    }
+    return WSB_OK;
+}
+
+static int sim_materialize_diagnostics(wsb_sim *s) {
+    if (!s->diag_dirty) return WSB_OK;
+    wsb_grid *g = &s->cur;
+    WSB_TRY(sim_ensure_halo(s));
+    if (s->comm) WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    s->diag_dirty = false;
+    return wsb_grid_calculate_diagnostics(g);
+}
+
+// ------------------------------------------------------------------------------ C-ABI: misc --
+extern "C" {
+
+const char *wsb_version(void) { return "weather_b200 0.1.0 (sm_100a)"; }
+
+const char *wsb_last_error(void) { return g_last_error.c_str(); }
+
+int wsb_device_count(int *count) {
+    if (!count) return fail(WSB_ERR_INVALID_ARGUMENT, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return WSB_OK;
+}
+
+int wsb_device_capabilities(int device_id, wsb_device_caps *out) {
+    if (!out) return fail(WSB_ERR_INVALID_ARGUMENT, "out is NULL");
+    std::memset(out, 0, sizeof(*out));
+    cudaDeviceProp p;
+    WSB_CUDA(cudaGetDeviceProperties(&p, device_id));
+    out->compute_capability_major = p.major;
+    out->compute_capability_minor = p.minor;
+    out->multiprocessors = p.multiProcessorCount;
+    out->cuda_cores = p.multiProcessorCount * 128;  // 128 FP32 lanes per SM on sm_80..sm_100
+    out->global_memory = p.totalGlobalMem;
+    out->shared_memory_per_block = p.sharedMemPerBlock;
+    out->max_threads_per_block = p.maxThreadsPerBlock;
+    out->max_threads_per_multiprocessor = p.maxThreadsPerMultiProcessor;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device_id) == cudaSuccess) out->clock_rate_khz = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMemoryClockRate, device_id) == cudaSuccess) out->memory_clock_rate_khz = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrGlobalMemoryBusWidth, device_id) == cudaSuccess) out->memory_bus_width = v;
+    cudaGetLastError();
+    // DeviceType (gpu_adaptability.hpp:23-30; detection rules gpu_adaptability.cpp:40-80)
+    if (p.major == 8 && p.minor == 7) out->device_type = 2;
+    else if (p.major == 7 && p.minor == 5) out->device_type = 3;
+    else if (p.major >= 8) out->device_type = 4;
+    else out->device_type = 5;
+    out->compute_power_ratio = (float)out->cuda_cores * (float)out->clock_rate_khz / (8.0f * 3.0e6f * 16.0f);
+    std::strncpy(out->device_name, p.name, sizeof(out->device_name) - 1);
+    return WSB_OK;
+}
+
+int wsb_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(WSB_ERR_INVALID_ARGUMENT, "out is NULL");
+    WSB_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return WSB_OK;
+}
+
+int wsb_host_free(void *ptr) {
+    if (ptr) WSB_CUDA(cudaFreeHost(ptr));
+    return WSB_OK;
+}
+
+int wsb_nccl_get_unique_id(void *out128) { return nccl_get_unique_id(out128); }
+
+int wsb_partition_rows(int32_t grid_height, int32_t nranks, int32_t rank, int32_t *row0, int32_t *nrows) {
+    if (grid_height <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || nranks > grid_height)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "invalid partition request");
+    const int base = grid_height / nranks, rem = grid_height % nranks;
+    if (nrows) *nrows = base + (rank < rem ? 1 : 0);
+    if (row0) *row0 = rank * base + std::min(rank, rem);
+    return WSB_OK;
+}
+
+// ------------------------------------------------------------------------------ C-ABI: grid --
+int wsb_grid_create(int32_t width, int32_t height, int32_t num_levels, double dx, double dy, int32_t dtype,
+                    int32_t device_id, wsb_grid **out) {
+    if (!out) return fail(WSB_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    std::unique_ptr<wsb_grid> g(new wsb_grid());
+    int st = grid_init(g.get(), width, height, num_levels, dx, dy, dtype, device_id, 0, height, nullptr);
+    if (st != WSB_OK) {
+        grid_fini(g.get());
+        return st;
+    }
+    *out = g.release();
+    return WSB_OK;
+}
+
+void wsb_grid_destroy(wsb_grid *grid) {
+    if (!grid || grid->owner) return;  // a simulation's grid dies with the simulation
+    cudaSetDevice(grid->device);
+    cudaStreamSynchronize(grid->stream);
+    grid_fini(grid);
+    delete grid;
+}
+
+int wsb_grid_reset(wsb_grid *g) {
+    if (!g) return fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
+    WSB_CUDA(cudaSetDevice(g->device));
+    for (int k = 0; k < WSB_NUM_FIELDS; ++k) {
+        if (k <= WSB_FIELD_HEIGHT) WSB_TRY(grid_fill(g, g->f[k].base, (double)kResetValue[k]));
+        else grid_release(g, k, (double)kResetValue[k]);
+    }
+    if (g->owner) {
+        g->owner->diag_dirty = false;
+        g->owner->halo_valid = false;
+    }
+    return WSB_OK;
+}
+
+int wsb_grid_get_info(const wsb_grid *g, wsb_grid_info *out) {
+    if (!g || !out) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    out->width = g->W; out->height = g->H; out->num_levels = g->L; out->dtype = g->dtype;
+    out->dx = g->dx; out->dy = g->dy; out->device_id = g->device; out->reserved = 0;
+    return WSB_OK;
+}
+
+int wsb_grid_set_spacing(wsb_grid *g, double dx, double dy) {
+    if (!g) return fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
+    if (!(dx > 0.0) || !(dy > 0.0))
+        return fail(WSB_ERR_INVALID_ARGUMENT, "Grid spacing must be positive");  // weather_grid.cpp:74-76
+    g->dx = g->dtype == WSB_F32 ? (double)(float)dx : dx;
+    g->dy = g->dtype == WSB_F32 ? (double)(float)dy : dy;
+    return WSB_OK;
+}
+
+static int check_shape(const wsb_grid *g, int64_t levels, int64_t rows, int64_t cols) {
+    if (rows != g->H || cols != g->W || levels != g->L)
+        return fail(WSB_ERR_RUNTIME, "Array dimensions must match field dimensions");  // python_bindings.cpp:70-72
+    return WSB_OK;
+}
+
+int wsb_grid_set_field(wsb_grid *g, int32_t field, const void *host, int32_t host_dtype, int64_t levels,
+                       int64_t rows, int64_t cols) {
+    if (!g || !host) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (field < 0 || field > WSB_FIELD_HUMIDITY) return fail(WSB_ERR_INVALID_ARGUMENT, "field cannot be set");
+    if (host_dtype != WSB_F32 && host_dtype != WSB_F64) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown host dtype");
+    WSB_TRY(check_shape(g, levels, rows, cols));
+    WSB_CUDA(cudaSetDevice(g->device));
+    if (g->owner && field <= WSB_FIELD_V) WSB_TRY(sim_materialize_diagnostics(g->owner));
+    if (!g->f[field].base) WSB_TRY(grid_alloc_plane(g, &g->f[field].base));
+    const size_t es = elem_size(g->dtype);
+    const size_t n = (size_t)levels * rows * cols;
+    const void *src = host;
+    std::vector<char> conv;
+    if (host_dtype != g->dtype) {  // forcecast, like py::array_t<scalar_t> (python_bindings.cpp:60)
+        conv.resize(n * es);
+        if (g->dtype == WSB_F32) {
+            const double *s = (const double *)host; float *d = (float *)conv.data();
+            for (size_t i = 0; i < n; ++i) d[i] = (float)s[i];
+        } else {
+            const float *s = (const float *)host; double *d = (double *)conv.data();
+            for (size_t i = 0; i < n; ++i) d[i] = (double)s[i];
+        }
+        src = conv.data();
+    }
+    WSB_CUDA(cudaEventRecord(g->ev0, g->stream));
+    for (int64_t l = 0; l < levels; ++l) {
+        char *dst = (char *)g->origin(field) + (size_t)l * g->level_stride * es;
+        const char *s = (const char *)src + (size_t)l * rows * cols * es;
+        WSB_CUDA(cudaMemcpy2DAsync(dst, (size_t)g->pitch * es, s, (size_t)cols * es, (size_t)cols * es, (size_t)rows,
+                                   cudaMemcpyHostToDevice, g->stream));
+    }
+    WSB_CUDA(cudaEventRecord(g->ev1, g->stream));
+    WSB_CUDA(cudaStreamSynchronize(g->stream));  // the host buffer is reusable on return
+    float ms = 0.f;
+    WSB_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+    g->transfer_ms += ms;
+    if (g->owner) {
+        g->owner->metrics.memory_transfer_time_ms += ms;
+        if (field <= WSB_FIELD_HEIGHT) g->owner->halo_valid = false;
+    }
+    return WSB_OK;
+}
+
+int wsb_grid_get_field(wsb_grid *g, int32_t field, void *host, int32_t host_dtype, int64_t levels, int64_t rows,
+                       int64_t cols) {
+    if (!g || !host) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (field < 0 || field >= WSB_NUM_FIELDS) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown field");
+    if (host_dtype != WSB_F32 && host_dtype != WSB_F64) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown host dtype");
+    WSB_TRY(check_shape(g, levels, rows, cols));
+    WSB_CUDA(cudaSetDevice(g->device));
+    if (g->owner && field >= WSB_FIELD_VORTICITY) WSB_TRY(sim_materialize_diagnostics(g->owner));
+    const size_t es = elem_size(g->dtype);
+    const size_t n = (size_t)levels * rows * cols;
+    if (!g->f[field].base) {  // never touched: uniformly its reset()/swap value
+        WSB_CUDA(cudaStreamSynchronize(g->stream));
+        if (host_dtype == WSB_F32) std::fill((float *)host, (float *)host + n, (float)g->f[field].uniform);
+        else std::fill((double *)host, (double *)host + n, g->f[field].uniform);
+        return WSB_OK;
+    }
+    std::vector<char> conv;
+    void *dst = host;
+    if (host_dtype != g->dtype) {
+        conv.resize(n * es);
+        dst = conv.data();
+    }
+    WSB_CUDA(cudaEventRecord(g->ev0, g->stream));
+    for (int64_t l = 0; l < levels; ++l) {
+        const char *s = (const char *)g->origin(field) + (size_t)l * g->level_stride * es;
+        char *d = (char *)dst + (size_t)l * rows * cols * es;
+        WSB_CUDA(cudaMemcpy2DAsync(d, (size_t)cols * es, s, (size_t)g->pitch * es, (size_t)cols * es, (size_t)rows,
+                                   cudaMemcpyDeviceToHost, g->stream));
+    }
+    WSB_CUDA(cudaEventRecord(g->ev1, g->stream));
+    WSB_CUDA(cudaStreamSynchronize(g->stream));
+    float ms = 0.f;
+    WSB_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+    g->transfer_ms += ms;
+    if (g->owner) g->owner->metrics.memory_transfer_time_ms += ms;
+    if (host_dtype != g->dtype) {
+        if (host_dtype == WSB_F32) {
+            const double *s = (const double *)conv.data(); float *d = (float *)host;
+            for (size_t i = 0; i < n; ++i) d[i] = (float)s[i];
+        } else {
+            const float *s = (const float *)conv.data(); double *d = (double *)host;
+            for (size_t i = 0; i < n; ++i) d[i] = (double)s[i];
+        }
+    }
+    return WSB_OK;
+}
+
+int wsb_grid_calculate_diagnostics(wsb_grid *g) {
+    if (!g) return fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
+    WSB_CUDA(cudaSetDevice(g->device));
+    for (int k = WSB_FIELD_VORTICITY; k <= WSB_FIELD_DIVERGENCE; ++k)
+        if (!g->f[k].base) WSB_TRY(grid_alloc_plane(g, &g->f[k].base));
+    if (g->owner) {
+        wsb_sim *s = g->owner;
+        WSB_TRY(sim_ensure_halo(s));
+        if (s->comm) WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        s->diag_dirty = false;
+    }
+    if (g->dtype == WSB_F64) {
+        WSB_CUDA(launch_diagnostics<double>(g->geom<double>(), g->physics<double>(0, 0), (const double *)g->origin(0),
+                                            (const double *)g->origin(1), (double *)g->origin(WSB_FIELD_VORTICITY),
+                                            (double *)g->origin(WSB_FIELD_DIVERGENCE), g->stream));
+    } else {
+        WSB_CUDA(launch_diagnostics<float>(g->geom<float>(), g->physics<float>(0, 0), (const float *)g->origin(0),
+                                           (const float *)g->origin(1), (float *)g->origin(WSB_FIELD_VORTICITY),
+                                           (float *)g->origin(WSB_FIELD_DIVERGENCE), g->stream));
+    }
+    return WSB_OK;
+}
+
+int wsb_grid_swap(wsb_grid *a, wsb_grid *b) {
+    if (!a || !b) return fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
+    if (a->W != b->W || a->H != b->H || a->L != b->L)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "Cannot swap grids of different dimensions");  // weather_grid.cpp:125-127
+    if (a->dtype != b->dtype || a->device != b->device)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "Cannot swap grids of different dtype or device");
+    if (a->owner) WSB_TRY(sim_materialize_diagnostics(a->owner));
+    if (b->owner) WSB_TRY(sim_materialize_diagnostics(b->owner));
+    WSB_CUDA(cudaStreamSynchronize(a->stream));
+    WSB_CUDA(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < WSB_NUM_FIELDS; ++k) std::swap(a->f[k], b->f[k]);
+    if (a->owner) a->owner->halo_valid = false;
+    if (b->owner) b->owner->halo_valid = false;
+    return WSB_OK;
+}
+
+int wsb_grid_device_pointer(wsb_grid *g, int32_t field, void **dev_ptr, int64_t *pitch_elems) {
+    if (!g || !dev_ptr) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (field < 0 || field >= WSB_NUM_FIELDS) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown field");
+    WSB_CUDA(cudaSetDevice(g->device));
+    if (g->owner && field >= WSB_FIELD_VORTICITY) WSB_TRY(sim_materialize_diagnostics(g->owner));
+    WSB_TRY(grid_materialize(g, field));
+    *dev_ptr = g->origin(field);
+    if (pitch_elems) *pitch_elems = g->pitch;
+    return WSB_OK;
+}
+
+// ------------------------------------------------------------------------------- C-ABI: sim --
+static void sim_free(wsb_sim *s) {
+    cudaSetDevice(s->cur.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->comm) halo_comm_destroy(s->comm);
+    sim_free3(s->next); sim_free3(s->tA); sim_free3(s->tB); sim_free3(s->k1); sim_free3(s->k2); sim_free3(s->k3);
+    for (int k = 0; k < WSB_NUM_FIELDS; ++k)
+        if (s->alt[k].base) cudaFree(s->alt[k].base);
+    if (s->d_partial) cudaFree(s->d_partial);
+    grid_fini(&s->cur);
+    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
+    if (!config || !out) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (config->struct_size != sizeof(wsb_config))
+        return fail(WSB_ERR_INVALID_ARGUMENT, "wsb_config.struct_size does not match this library");
+    wsb_config c = *config;
+    if (c.grid_width <= 0 || c.grid_height <= 0 || c.num_levels <= 0)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "Grid dimensions must be positive");  // weather_grid.cpp:50-52
+    if (c.dtype != WSB_F32 && c.dtype != WSB_F64) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown dtype");
+    if (c.model < 0 || c.model > WSB_MODEL_GENERAL) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown model");
+    if (c.integration_method < 0 || c.integration_method > WSB_INT_SEMI_IMPLICIT)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "unknown integration method");
+    if (c.nranks < 1) c.nranks = 1;
+    if (c.rank < 0 || c.rank >= c.nranks) return fail(WSB_ERR_INVALID_ARGUMENT, "rank out of range");
+    if (c.nranks > 1 && c.num_levels != 1)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "row-slab decomposition supports num_levels == 1 only");
+    if (c.nranks > 1 && !c.nccl_unique_id) return fail(WSB_ERR_INVALID_ARGUMENT, "nccl_unique_id is required when nranks > 1");
+    if (c.nranks > c.grid_height) return fail(WSB_ERR_INVALID_ARGUMENT, "more ranks than grid rows");
+
+    wsb_sim *s = new wsb_sim();
+    s->cfg = c;
+    s->cfg.nccl_unique_id = nullptr;
+    s->dtype = c.dtype;
+    if (c.dtype == WSB_F32) {  // the reference's config fields are float (weather_sim.hpp:166-172)
+        s->cfg.dt = (double)(float)c.dt; s->cfg.gravity = (double)(float)c.gravity;
+        s->cfg.coriolis_f = (double)(float)c.coriolis_f; s->cfg.max_time = (double)(float)c.max_time;
+    }
+    s->dt = s->cfg.dt;
+    s->nstages = effective_stages(c);
+    wsb_partition_rows(c.grid_height, c.nranks, c.rank, &s->row0, &s->nrows);
+
+    int st = WSB_OK;
+    do {
+        if (cudaSetDevice(c.device_id) != cudaSuccess) {
+            cudaGetLastError();
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+                cudaGetLastError();
+                st = fail(WSB_ERR_CUDA, "no CUDA device available: libweather_b200 has no CPU fallback");
+            } else {
+                st = fail(WSB_ERR_INVALID_ARGUMENT, "device_id out of range");
+            }
+            break;
+        }
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            st = fail(WSB_ERR_CUDA, "no CUDA device available: libweather_b200 has no CPU fallback");
+            break;
+        }
+        st = grid_init(&s->cur, c.grid_width, s->nrows, c.num_levels, c.dx, c.dy, c.dtype, c.device_id, s->row0,
+                       c.grid_height, s->stream);
+        if (st != WSB_OK) break;
+        s->cur.owner = s;
+        for (int k = 0; k < WSB_NUM_FIELDS; ++k) s->alt[k].uniform = (double)kResetValue[k];
+        cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1};
+        for (cudaEvent_t *e : evs)
+            if (cudaEventCreate(e) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
+        if (st != WSB_OK) break;
+
+        // kernel path
+        int want = c.kernel_variant;
+        if (want == WSB_KERNEL_AUTO)
+            want = step_fused_supported(s->nstages, s->dtype) ? WSB_KERNEL_STEP_FUSED : WSB_KERNEL_STAGE_DIRECT;
+        if (want == WSB_KERNEL_STEP_FUSED) {
+            if (!step_fused_supported(s->nstages, s->dtype)) {
+                st = fail(WSB_ERR_INVALID_ARGUMENT, "kernel_variant STEP_FUSED is not available for this configuration");
+                break;
+            }
+            s->path = PATH_STEP_FUSED;
+        } else if (want == WSB_KERNEL_STAGE_TMA) {
+            st = fail(WSB_ERR_INVALID_ARGUMENT, "kernel_variant STAGE_TMA is not built into this library");
+            break;
+        } else if (want == WSB_KERNEL_STAGE_DIRECT) {
+            s->path = PATH_STAGE_DIRECT;
+        } else {
+            st = fail(WSB_ERR_INVALID_ARGUMENT, "unknown kernel_variant");
+            break;
+        }
+        if (s->nrows < (s->path == PATH_STEP_FUSED ? s->nstages : 1) && c.nranks > 1) {
+            st = fail(WSB_ERR_INVALID_ARGUMENT, "row slab thinner than the ghost depth");
+            break;
+        }
+
+        if ((st = sim_alloc3(s, s->next)) != WSB_OK) break;
+        if (s->path != PATH_STEP_FUSED) {
+            if (s->nstages >= 2 && (st = sim_alloc3(s, s->tA)) != WSB_OK) break;
+            if (s->nstages == 4) {
+                if ((st = sim_alloc3(s, s->tB)) != WSB_OK) break;
+                if ((st = sim_alloc3(s, s->k2)) != WSB_OK) break;
+                if ((st = sim_alloc3(s, s->k3)) != WSB_OK) break;
+                if (c.rk4_mode == WSB_RK4_CLASSICAL && (st = sim_alloc3(s, s->k1)) != WSB_OK) break;
+            }
+        }
+        // ghost rows of scratch planes are read at slab edges before being written on rank 0 / G-1: zero them
+        void **sets[] = {s->next, s->tA, s->tB};
+        for (void **set : sets)
+            for (int k = 0; k < 3; ++k)
+                if (set[k] && (st = grid_fill(&s->cur, set[k], 0.0)) != WSB_OK) break;
+        if (st != WSB_OK) break;
+
+        if (c.nranks > 1) {
+            if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                st = cuda_fail(cudaGetLastError(), "cudaStreamCreate(comm)", __FILE__, __LINE__);
+                break;
+            }
+            if ((st = halo_comm_create(c.rank, c.nranks, c.nccl_unique_id, &s->comm)) != WSB_OK) break;
+        }
+        s->npartial = 1024;
+        if (cudaMalloc(&s->d_partial, sizeof(double) * 2 * s->npartial) != cudaSuccess) {
+            st = cuda_fail(cudaGetLastError(), "cudaMalloc(partials)", __FILE__, __LINE__);
+            break;
+        }
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) {
+            st = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
+            break;
+        }
+    } while (0);
+    if (st != WSB_OK) {
+        std::string keep = g_last_error;
+        sim_free(s);
+        g_last_error = keep;
+        return st;
+    }
+    *out = s;
+    return WSB_OK;
+}
+
+void wsb_sim_destroy(wsb_sim *sim) {
+    if (sim) sim_free(sim);
+}
+
+int wsb_sim_initialize(wsb_sim *s) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    WSB_TRY(sim_sync(s));
+    s->time = 0.0;
+    s->step = 0;
+    std::memset(&s->metrics, 0, sizeof(s->metrics));
+    return wsb_grid_reset(&s->cur);
+}
+
+wsb_grid *wsb_sim_current_grid(wsb_sim *s) { return s ? &s->cur : nullptr; }
+
+int wsb_sim_advance_async(wsb_sim *s, int32_t num_steps) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    WSB_CUDA(cudaSetDevice(s->cur.device));
+    WSB_TRY(sim_begin_timing(s));
+    for (int i = 0; i < num_steps; ++i) WSB_TRY(sim_enqueue_step(s));
+    return WSB_OK;
+}
+
+int wsb_sim_synchronize(wsb_sim *s) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    return sim_sync(s);
+}
+
+int wsb_sim_step(wsb_sim *s) {
+    WSB_TRY(wsb_sim_advance_async(s, 1));
+    return sim_sync(s);
+}
+
+int wsb_sim_run(wsb_sim *s, int32_t num_steps, int32_t *steps_done) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    if (steps_done) *steps_done = 0;
+    if (num_steps <= 0) return WSB_OK;  // weather_simulation.cpp:69-71
+    WSB_CUDA(cudaSetDevice(s->cur.device));
+    const auto t0 = std::chrono::steady_clock::now();
+    WSB_TRY(sim_begin_timing(s));
+    int done = 0;
+    for (int i = 0; i < num_steps; ++i) {
+        WSB_TRY(sim_enqueue_step(s));
+        ++done;
+        if (s->time >= s->cfg.max_time) break;  // :87-89, checked after the step
+    }
+    WSB_TRY(sim_sync(s));
+    const auto t1 = std::chrono::steady_clock::now();
+    s->metrics.total_time_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (steps_done) *steps_done = done;
+    return WSB_OK;
+}
+
+int wsb_sim_run_until(wsb_sim *s, double max_time, int32_t *steps_done) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    if (steps_done) *steps_done = 0;
+    int n;
+    if (s->dtype == WSB_F32) {  // weather_simulation.cpp:105-115 in float
+        const float mt = (float)max_time, t = (float)s->time, dt = (float)s->dt;
+        if (mt <= t) return WSB_OK;
+        n = (int)((mt - t) / dt) + 1;
+    } else {
+        if (max_time <= s->time) return WSB_OK;
+        n = (int)((max_time - s->time) / s->dt) + 1;
+    }
+    return wsb_sim_run(s, n, steps_done);
+}
+
+int wsb_sim_last_run_device_ms(wsb_sim *s, double *ms) {
+    if (!s || !ms) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *ms = s->last_run_ms;
+    return WSB_OK;
+}
+
+double wsb_sim_get_time(const wsb_sim *s) { return s ? s->time : 0.0; }
+int32_t wsb_sim_get_step(const wsb_sim *s) { return s ? s->step : 0; }
+double wsb_sim_get_dt(const wsb_sim *s) { return s ? s->dt : 0.0; }
+
+int wsb_sim_set_dt(wsb_sim *s, double dt) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    s->dt = s->dtype == WSB_F32 ? (double)(float)dt : dt;
+    return WSB_OK;
+}
+
+int wsb_sim_get_config(const wsb_sim *s, wsb_config *out) {
+    if (!s || !out) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = s->cfg;
+    return WSB_OK;
+}
+
+int wsb_sim_get_metrics(wsb_sim *s, wsb_metrics *out) {
+    if (!s || !out) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = s->metrics;
+    return WSB_OK;
+}
+
+int wsb_sim_reset_metrics(wsb_sim *s) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    std::memset(&s->metrics, 0, sizeof(s->metrics));
+    return WSB_OK;
+}
+
+int wsb_sim_local_rows(const wsb_sim *s, int32_t *row0, int32_t *nrows) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    if (row0) *row0 = s->row0;
+    if (nrows) *nrows = s->nrows;
+    return WSB_OK;
+}
+
+const char *wsb_sim_kernel_name(const wsb_sim *s) {
+    if (!s) return "";
+    switch (s->path) {
+        case PATH_STEP_FUSED: return "step_fused";
+        case PATH_STAGE_TMA: return "stage_tma";
+        default: return "stage_direct";
+    }
+}
+
+int wsb_sim_mass_energy(wsb_sim *s, double *mass, double *energy) {
+    if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
+    WSB_CUDA(cudaSetDevice(s->cur.device));
+    const wsb_grid *g = &s->cur;
+    if (s->dtype == WSB_F64) {
+        WSB_CUDA(launch_mass_energy<double>(g->geom<double>(), (const double *)g->origin(0), (const double *)g->origin(1),
+                                            (const double *)g->origin(2), s->cfg.gravity, s->d_partial, s->npartial,
+                                            s->stream));
+    } else {
+        WSB_CUDA(launch_mass_energy<float>(g->geom<float>(), (const float *)g->origin(0), (const float *)g->origin(1),
+                                           (const float *)g->origin(2), s->cfg.gravity, s->d_partial, s->npartial,
+                                           s->stream));
+    }
+    std::vector<double> hp(2 * s->npartial);
+    WSB_CUDA(cudaMemcpyAsync(hp.data(), s->d_partial, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    WSB_CUDA(cudaStreamSynchronize(s->stream));
+    double m = 0.0, e = 0.0;
+    for (int b = 0; b < s->npartial; ++b) {
+        m += hp[2 * b];
+        e += hp[2 * b + 1];
+    }
+    if (mass) *mass = m;
+    if (energy) *energy = e;
+    return WSB_OK;
+}
+
+}  // extern "C"

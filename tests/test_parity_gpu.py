@@ -1,0 +1,358 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI (ctypes), against the CPU oracle and
+the committed reference-generated golden vectors. Bit-exact is the bar (fp32 and fp64: same operation
+order, no contraction); the north-star tolerances (rel-L2 <= 1e-5 fp32 / 1e-12 fp64, mass and energy to
+the same bound) are asserted on top where the test states them.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_py import Oracle
+from weather_sim import _capi
+from weather_sim import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("u", "v", "h", "p", "t", "q", "vorticity")
+VARIANTS = ("stage_direct", "step_fused")
+MODELS = ("shallow_water", "barotropic", "primitive", "general")
+INTEGRATORS = ("euler", "rk2", "rk4", "adams_bashforth", "semi_implicit")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def assert_bit_equal(a, b, what=""):
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    same = bits(a) == bits(b)
+    if not same.all():
+        bad = np.argwhere(~same)
+        raise AssertionError(
+            f"{what}: {len(bad)} of {a.size} cells differ, first at {tuple(bad[0])}: {a[tuple(bad[0])]!r} vs "
+            f"{b[tuple(bad[0])]!r}; rel-L2 {syn.rel_l2(a, b):.3e}")
+
+
+def cuda_sim(W, H, model=0, integ=2, kernel="auto", **kw):
+    return _capi.Simulation(W, H, model=model, integrator=integ, kernel=kernel, max_time=1e30, **kw)
+
+
+def compare_with_oracle(W, H, model, integ, kernel, steps, ic, dtype=np.float32, fields=("u", "v", "h", "vorticity"),
+                        **phys):
+    u, v, h = ic
+    o = Oracle(W, H, model, integ, dtype=dtype, **phys)
+    s = cuda_sim(W, H, model, integ, kernel, dtype=dtype, **phys)
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    o.step(steps)
+    s.step(steps)
+    for name in fields:
+        assert_bit_equal(s.get_field(name), o.get_field(name), f"{W}x{H} m{model} i{integ} {kernel} {name}")
+    assert s.steps == o.steps
+    assert s.time == o.time
+    s.close()
+    o.close()
+
+
+# ---------------------------------------------------------------------------- golden vectors --
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_small_matrix_golden(golden_dir, kernel):
+    """Every (model, integrator) pair x f in {0, 0.1}: 17x13 white noise (dx=0.75, dy=1.3 -> true division
+    path) and 64x48 Gaussian bump (dx=dy=1 -> exact-reciprocal path), 5 steps, all seven fields."""
+    g = np.load(os.path.join(golden_dir, "small_matrix.npz"))
+    for key, params in zip(g["cases"], g["case_params"]):
+        W, H, model, integ, f, dx, dy, steps = params
+        W, H, model, integ, steps = int(W), int(H), int(model), int(integ), int(steps)
+        s = cuda_sim(W, H, model, integ, kernel, dx=dx, dy=dy, coriolis_f=f)
+        s.set_state(g[f"in_{W}x{H}_u"], g[f"in_{W}x{H}_v"], g[f"in_{W}x{H}_h"])
+        s.step(steps)
+        for name in FIELDS:
+            assert_bit_equal(s.get_field(name), g[f"{key}_{name}"], f"{key}/{name}/{kernel}")
+        s.close()
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_edge_shapes_golden(golden_dir, kernel):
+    """Degenerate grids 1x1, 1x9, 9x1, 2x2, 3x2: every neighbour clamps onto the cell itself."""
+    g = np.load(os.path.join(golden_dir, "edge_shapes.npz"))
+    for key in g["cases"]:
+        shape, integ = key.split("_i")
+        W, H = (int(x) for x in shape.split("x"))
+        s = cuda_sim(W, H, 0, int(integ), kernel, coriolis_f=0.1)
+        s.set_state(g[f"{key}_in_u"], g[f"{key}_in_v"], g[f"{key}_in_h"])
+        s.step(3)
+        for name in ("u", "v", "h", "vorticity"):
+            assert_bit_equal(s.get_field(name), g[f"{key}_{name}"], f"{key}/{name}/{kernel}")
+        s.close()
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+@pytest.mark.parametrize("f", [0.0, 0.1])
+def test_config1_swe256_euler1000(golden_dir, kernel, f):
+    """BASELINE config 1 exactly: SWE 256x256 fp32 Euler 1000 steps, Gaussian bump, vs the reference's output.
+    Tolerance stated by the north star: rel-L2 <= 1e-5 per field + mass/energy; measured: bit-exact."""
+    g = np.load(os.path.join(golden_dir, "c1_swe256_euler1000.npz"))
+    u, v, h = syn.gaussian_bump(256, 256)
+    s = cuda_sim(256, 256, 0, 0, kernel, coriolis_f=f)
+    s.set_state(u, v, h)
+    s.step(1000)
+    st = {n: s.get_field(n) for n in ("u", "v", "h", "vorticity")}
+    for n, a in st.items():
+        assert syn.rel_l2(a, g[f"f{f}_{n}"]) <= 1e-5
+        assert_bit_equal(a, g[f"f{f}_{n}"], f"c1 f={f} {n} {kernel}")
+    mass, energy = syn.total_mass(st["h"]), syn.total_energy(st["u"], st["v"], st["h"])
+    assert abs(mass - float(g[f"f{f}_mass"])) <= 1e-5 * abs(mass)
+    assert abs(energy - float(g[f"f{f}_energy"])) <= 1e-5 * abs(energy)
+    dm, de = s.mass_energy()  # device-side fp64 reduction agrees with the host sums
+    assert abs(dm - mass) <= 1e-12 * abs(mass) and abs(de - energy) <= 1e-12 * abs(energy)
+    assert np.float32(s.time) == g[f"f{f}_time"]
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_rk4_swe128_golden(golden_dir, kernel):
+    g = np.load(os.path.join(golden_dir, "rk4_swe128_200.npz"))
+    u, v, h = syn.gaussian_bump(128, 128)
+    s = cuda_sim(128, 128, 0, 2, kernel, coriolis_f=0.1)
+    s.set_state(u, v, h)
+    s.step(200)
+    for n in ("u", "v", "h", "vorticity"):
+        assert_bit_equal(s.get_field(n), g[n], f"rk4 128 {n} {kernel}")
+    s.close()
+
+
+# ------------------------------------------------------------------------- against the oracle --
+SHAPES = [(55, 9), (56, 130), (57, 131), (111, 5), (112, 257), (113, 64), (300, 77), (1000, 3), (3, 1000), (60, 60),
+          (61, 7), (124, 10), (129, 300)]
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+@pytest.mark.parametrize("integ", [0, 1, 2])
+def test_ragged_shapes_vs_oracle(kernel, integ):
+    """Widths around the fused kernel's strip widths (56/60-column outputs), odd widths (unaligned row ends),
+    heights around the 128-row chunk; non-power-of-two spacing (IEEE division path) and f != 0."""
+    for (W, H) in SHAPES:
+        ic = syn.white_noise_state(W, H, seed=W * 7 + H)
+        compare_with_oracle(W, H, 0, integ, kernel, 3, ic, dx=0.8, dy=1.7, dt=0.013, coriolis_f=0.21, gravity=9.81)
+        compare_with_oracle(W, H, 0, integ, kernel, 3, ic, dx=1.0, dy=0.5, coriolis_f=0.0)
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_swe_rk4_1024_200_steps_vs_oracle(kernel):
+    """SURVEY.md C2 parity leg: the 8192^2 benchmark code path on 1024^2 for 200 RK4 steps."""
+    W = H = 1024
+    u, v, h = syn.gaussian_bump(W, H)
+    o = Oracle(W, H, 0, 2, coriolis_f=0.1)
+    s = cuda_sim(W, H, 0, 2, kernel, coriolis_f=0.1)
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    o.step(200, diagnostics=False)
+    o.diagnostics()
+    s.step(200)
+    so = o.state()
+    ss = s.state()
+    for n in ("u", "v", "h"):
+        assert syn.rel_l2(ss[n], so[n]) <= 1e-5
+        assert_bit_equal(ss[n], so[n], f"1024 rk4 {n} {kernel}")
+    assert_bit_equal(s.get_field("vorticity"), o.get_field("vorticity"), "vorticity")
+    assert abs(syn.total_mass(ss["h"]) - syn.total_mass(so["h"])) <= 1e-5 * syn.total_mass(so["h"])
+    assert abs(syn.total_energy(**ss) - syn.total_energy(**so)) <= 1e-5 * syn.total_energy(**so)
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_random_vorticity_50_steps(kernel):
+    W, H = 384, 256
+    ic = syn.random_vorticity(W, H)
+    compare_with_oracle(W, H, 0, 2, kernel, 50, ic, coriolis_f=0.05)
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+@pytest.mark.parametrize("integ", [0, 1, 2])
+def test_fp64_vs_oracle(kernel, integ):
+    """fp64 path (BASELINE config 3: Barotropic, RK4 request -> RK2 semantics). North-star bound 1e-12; bit-exact."""
+    for (W, H) in ((130, 70), (33, 140)):
+        ic = tuple(a.astype(np.float64) for a in syn.random_vorticity(W, H, dtype=np.float64))
+        compare_with_oracle(W, H, 1, integ, kernel, 10, ic, dtype=np.float64, dx=0.9, dy=1.1, coriolis_f=0.1)
+        compare_with_oracle(W, H, 0, integ, kernel, 10, ic, dtype=np.float64, coriolis_f=0.1)
+
+
+def test_barotropic_fp64_1024_vs_oracle():
+    W = H = 1024
+    ic = syn.random_vorticity(W, H, dtype=np.float64)
+    u, v, h = ic
+    o = Oracle(W, H, 1, 2, dtype=np.float64)
+    s = cuda_sim(W, H, 1, 2, "auto", dtype=np.float64)
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    o.step(50, diagnostics=False)
+    s.step(50)
+    for n in ("u", "v", "h"):
+        assert syn.rel_l2(s.get_field(n), o.get_field(n)) <= 1e-12
+        assert_bit_equal(s.get_field(n), o.get_field(n), n)
+    s.close()
+
+
+def test_rk4_classical_opt_in_vs_oracle():
+    W, H = 90, 70
+    ic = syn.gaussian_bump(W, H)
+    u, v, h = ic
+    o = Oracle(W, H, 0, 2, rk4_classical=True, coriolis_f=0.1)
+    s = cuda_sim(W, H, 0, 2, "stage_direct", rk4_classical=True, coriolis_f=0.1)
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    o.step(20)
+    s.step(20)
+    for n in ("u", "v", "h"):
+        assert_bit_equal(s.get_field(n), o.get_field(n), n)
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", VARIANTS)
+def test_primitive_levels_vs_2d_oracle(kernel):
+    """BASELINE config 4 at test size: Primitive 256x256x4 levels, each level == the 2-D oracle (the reference
+    has no vertical coupling); T and p drift by the constant reset() tendencies."""
+    W = H = 256
+    L = 4
+    u0, v0, h0 = syn.gaussian_bump(W, H)
+    hs = np.stack([10.0 + (1.0 + k / 64.0) * (h0.astype(np.float64) - 10.0) for k in range(L)]).astype(np.float32)
+    us = np.stack([u0] * L)
+    vs = np.stack([v0] * L)
+    for integ in (0, 1):
+        s = cuda_sim(W, H, 2, integ, kernel, num_levels=L)
+        s.set_state(us, vs, hs)
+        s.step(10)
+        got = {n: s.get_field(n) for n in ("u", "v", "h", "t", "p", "vorticity")}
+        for k in range(L):
+            o = Oracle(W, H, 2, integ)
+            o.set_state(us[k], vs[k], hs[k])
+            o.step(10)
+            for n in got:
+                assert_bit_equal(got[n][k], o.get_field(n), f"level {k} {n} integ {integ} {kernel}")
+        s.close()
+
+
+# ------------------------------------------------------------------ driver semantics / quirks --
+def test_untouched_fields_alternate_like_the_reference():
+    """The reference swaps whole grids every step: p/T/q written into 'current' reappear on even steps."""
+    W, H = 16, 8
+    o = Oracle(W, H, 0, 0)
+    s = cuda_sim(W, H, 0, 0)
+    p = np.arange(W * H, dtype=np.float32).reshape(H, W)
+    o.set_field("p", p)
+    s.grid.set_field("p", p)
+    for k in range(1, 4):
+        o.step(1)
+        s.step(1)
+        for n in ("p", "t", "q"):
+            assert_bit_equal(s.get_field(n), o.get_field(n), f"step {k} {n}")
+    s.close()
+
+
+def test_run_stops_at_max_time_like_the_reference():
+    """weather_simulation.cpp:87-89: with dt = 0.01f and max_time = 10 exactly 1000 steps run."""
+    s = _capi.Simulation(32, 32, integrator="euler", max_time=10.0)
+    done = s.run(1500)
+    assert done == 1000 and s.steps == 1000
+    assert np.float32(s.time) >= np.float32(10.0)
+    assert s.run(5) == 1  # every further run() performs one step, then breaks
+    s.close()
+    s = _capi.Simulation(32, 32, integrator="euler", max_time=1e30)
+    done = s.run_until(0.255)  # int((0.255 - 0)/0.01f) + 1 in float arithmetic (:111)
+    assert done == int((np.float32(0.255) - np.float32(0)) / np.float32(0.01)) + 1
+    s.close()
+
+
+def test_set_dt_and_metrics():
+    s = cuda_sim(64, 64, 0, 2)
+    o = Oracle(64, 64, 0, 2)
+    ic = syn.gaussian_bump(64, 64)
+    s.set_state(*ic)
+    o.set_state(*ic)
+    s.set_dt(0.02)
+    o.set_dt(0.02)
+    s.step(3)
+    o.step(3)
+    assert_bit_equal(s.get_field("h"), o.get_field("h"), "h after set_dt")
+    assert s.time == o.time
+    m = s.metrics
+    assert m.num_steps == 3 and m.compute_time_ms > 0 and m.kernel_launches >= 3 and m.memory_transfer_time_ms > 0
+    s.reset_metrics()
+    assert s.metrics.num_steps == 0
+    s.close()
+
+
+def test_grid_api_errors_and_diagnostics():
+    g = _capi.Grid(20, 10)
+    assert g.get_field("h").shape == (10, 20) and (g.get_field("h") == 10.0).all()
+    assert (g.get_field("p") == np.float32(1013.25)).all() and (g.get_field("t") == np.float32(288.15)).all()
+    with pytest.raises(RuntimeError, match="Array dimensions must match field dimensions"):
+        g.set_field("h", np.zeros((20, 10), np.float32))
+    with pytest.raises(ValueError, match="Grid spacing must be positive"):
+        g.set_spacing(0.0, 1.0)
+    # vorticity sign of a counter-clockwise vortex (weather_grid_test.cpp:81-111)
+    y, x = np.mgrid[0:10, 0:20].astype(np.float32)
+    u, v = -(y - 4.5), (x - 9.5)
+    g.set_field("u", u)
+    g.set_field("v", v)
+    g.calculate_diagnostics()
+    o = Oracle(20, 10)
+    o.set_state(u, v, np.full((10, 20), 10.0, np.float32))
+    o.diagnostics()
+    assert_bit_equal(g.get_field("vorticity"), o.get_field("vorticity"), "vorticity")
+    assert_bit_equal(g.get_field("divergence"), o.get_field("divergence"), "divergence")
+    assert g.get_field("vorticity")[5, 10] > 0
+    # float64 input is accepted and cast, like pybind's forcecast
+    g.set_field("h", np.full((10, 20), 3.0, np.float64))
+    assert (g.get_field("h") == 3.0).all()
+    g2 = _capi.Grid(21, 10)
+    with pytest.raises(ValueError, match="Cannot swap grids of different dimensions"):
+        g.swap(g2)
+    g3 = _capi.Grid(20, 10)
+    g.swap(g3)
+    assert (g.get_field("h") == 10.0).all() and (g3.get_field("h") == 3.0).all()
+    g.reset()
+    assert (g.get_field("u") == 0).all()
+    for x_ in (g, g2, g3):
+        x_.close()
+
+
+# -------------------------------------------------------------- full benchmark size properties --
+def test_full_size_8192_step_fused_equals_stage_path_and_oracle_crops():
+    """BASELINE config 2 size (SWE 8192x8192 fp32 RK4). Size-independent properties:
+    (1) the whole-step fused kernel and the per-stage path agree bit-for-bit after 2 steps;
+    (2) a step only depends on a 4-cell neighbourhood, so the interior of an oracle run on a crop of the
+        initial state must equal the same window of the full-size result (checked at the four corners,
+        which include the clamped edges, and at an interior window crossing strip and chunk seams);
+    (3) mass and energy of both paths are identical."""
+    W = H = 8192
+    u, v, h = syn.gaussian_bump(W, H, sigma_frac=0.02)
+    # add deterministic small-scale structure so every stencil term is exercised everywhere
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    u = (u + np.float32(0.05) * np.sin(xx * np.float32(0.37)) * np.cos(yy * np.float32(0.21))).astype(np.float32)
+    v = (v + np.float32(0.05) * np.cos(xx * np.float32(0.11)) * np.sin(yy * np.float32(0.43))).astype(np.float32)
+    del xx, yy
+    res = {}
+    for kernel in VARIANTS:
+        s = cuda_sim(W, H, 0, 2, kernel, coriolis_f=0.1)
+        s.set_state(u, v, h)
+        s.step(2)
+        res[kernel] = s.state()
+        res[kernel + "_me"] = s.mass_energy()
+        s.close()
+    for n in ("u", "v", "h"):
+        assert_bit_equal(res["step_fused"][n], res["stage_direct"][n], f"8192 {n}")
+    assert res["step_fused_me"] == res["stage_direct_me"]
+    C, R = 160, 8  # crop size, dependency radius of 2 RK4 steps
+    windows = [(0, 0), (0, W - C), (H - C, 0), (H - C, W - C), (4000, 4400), (120, 3300)]
+    for (y0, x0) in windows:
+        o = Oracle(C, C, 0, 2, coriolis_f=0.1)
+        o.set_state(u[y0:y0 + C, x0:x0 + C], v[y0:y0 + C, x0:x0 + C], h[y0:y0 + C, x0:x0 + C])
+        o.step(2, diagnostics=False)
+        ys = slice(0 if y0 == 0 else R, C if y0 + C == H else C - R)
+        xs = slice(0 if x0 == 0 else R, C if x0 + C == W else C - R)
+        for n in ("u", "v", "h"):
+            full = res["step_fused"][n][y0:y0 + C, x0:x0 + C]
+            assert_bit_equal(np.ascontiguousarray(full[ys, xs]), np.ascontiguousarray(o.get_field(n)[ys, xs]),
+                             f"crop ({y0},{x0}) {n}")
