@@ -220,9 +220,9 @@ def run_b200_arm(args, rank, world, local_rank):
     halo_ms = sim.metrics.halo_time_ms
 
     # ---- end to end through the C-ABI with HOST buffers: H2D state, one step, D2H state, every step ----
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 10))
     outs = [_capi.pinned_empty((nrows, GRID_W), np.float32) for _ in range(3)]
-    for _ in range(2):  # warm-up of the copy path
+    for _ in range(2 if e2e_steps else 0):  # warm-up of the copy path
         sim.set_state(ub, vb, hb)
         sim.step(1)
         for n, o in zip(("u", "v", "h"), outs):
@@ -236,7 +236,7 @@ def run_b200_arm(args, rank, world, local_rank):
             sim.get_field(n, out=o)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = cells_total * e2e_steps / e2e_s
+    e2e_value = cells_total * e2e_steps / e2e_s if e2e_steps else None
     field_bytes = nrows * GRID_W * 4
 
     if rank == 0:
@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "stage_direct", "step_fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

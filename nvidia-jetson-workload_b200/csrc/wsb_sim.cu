@@ -819,10 +819,12 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
 
         // kernel path
         int want = c.kernel_variant;
-        if (want == WSB_KERNEL_AUTO)
-            want = step_fused_supported(s->nstages, s->dtype) ? WSB_KERNEL_STEP_FUSED : WSB_KERNEL_STAGE_DIRECT;
+        // the whole-step kernel implements the reference (aliased) RK4 combine only
+        const bool fused_ok = step_fused_supported(s->nstages, s->dtype) &&
+                              !(s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL);
+        if (want == WSB_KERNEL_AUTO) want = fused_ok ? WSB_KERNEL_STEP_FUSED : WSB_KERNEL_STAGE_DIRECT;
         if (want == WSB_KERNEL_STEP_FUSED) {
-            if (!step_fused_supported(s->nstages, s->dtype)) {
+            if (!fused_ok) {
                 st = fail(WSB_ERR_INVALID_ARGUMENT, "kernel_variant STEP_FUSED is not available for this configuration");
                 break;
             }

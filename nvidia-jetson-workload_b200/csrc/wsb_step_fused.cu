@@ -285,13 +285,9 @@ struct Sweep {
     }
 };
 
-template <int NST>
-constexpr int min_blocks() {
-    return NST == 4 ? 3 : 4;
-}
-
-template <typename T, int NST, int V, bool RECIP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks<NST>())
+// MINB = minimum resident CTAs (= warps) per SM the register allocator must allow: 65536 / (32 * MINB) registers.
+template <typename T, int NST, int V, bool RECIP, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
     step_fused_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk) {
     constexpr int SW = 32 * V;
     constexpr int HX = (NST + V - 1) / V * V;  // halo columns per side, a multiple of V so vector loads stay aligned
@@ -319,28 +315,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks<NST>())
     sw.run();
 }
 
-int rows_per_chunk_default(int rows) {
-    static int env = -1;
-    if (env < 0) {
-        const char *e = std::getenv("WSB_FUSED_ROWS_PER_CHUNK");
-        env = e ? std::atoi(e) : 0;
-    }
-    if (env > 0) return env;
-    (void)rows;
-    return 128;
+int env_int(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
 }
 
-template <typename T, int NST, int V>
+// tuning knobs (read once): rows each warp sweeps, and the occupancy variant of the RK4 kernel
+int rows_per_chunk_default() {
+    static const int v = env_int("WSB_FUSED_ROWS_PER_CHUNK", 128);
+    return v > 0 ? v : 128;
+}
+
+int minb_variant() {
+    static const int v = env_int("WSB_FUSED_MINB", 0);
+    return v;
+}
+
+template <typename T, int NST, int V, int MINB>
 cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
     const int rows = a.y_end - a.y_begin;
     if (rows <= 0) return cudaSuccess;
     constexpr int OUTW = 32 * V - 2 * ((NST + V - 1) / V * V);
     const int strips = (g.W + OUTW - 1) / OUTW;
-    const int rpc = rows_per_chunk_default(rows);
+    const int rpc = rows_per_chunk_default();
     const dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, (rows + rpc - 1) / rpc, g.L);
     const dim3 block(kWarpsPerCta * 32);
-    if (ph.recip) step_fused_kernel<T, NST, V, true><<<grid, block, 0, st>>>(g, ph, a, rpc);
-    else step_fused_kernel<T, NST, V, false><<<grid, block, 0, st>>>(g, ph, a, rpc);
+    if (ph.recip) step_fused_kernel<T, NST, V, true, MINB><<<grid, block, 0, st>>>(g, ph, a, rpc);
+    else step_fused_kernel<T, NST, V, false, MINB><<<grid, block, 0, st>>>(g, ph, a, rpc);
     return cudaGetLastError();
 }
 
@@ -357,9 +358,14 @@ cudaError_t launch_step_fused<float>(const Geometry<float> &g, const Physics<flo
                                      int nstages, cudaStream_t st) {
     if (a.classical && nstages == 4) return cudaErrorNotSupported;
     switch (nstages) {
-        case 1: return launch_impl<float, 1, 2>(g, ph, a, st);
-        case 2: return launch_impl<float, 2, 2>(g, ph, a, st);
-        case 4: return launch_impl<float, 4, 2>(g, ph, a, st);
+        case 1: return launch_impl<float, 1, 2, 16>(g, ph, a, st);
+        case 2: return launch_impl<float, 2, 2, 12>(g, ph, a, st);
+        case 4:
+            switch (minb_variant()) {
+                case 12: return launch_impl<float, 4, 2, 12>(g, ph, a, st);
+                case 16: return launch_impl<float, 4, 2, 16>(g, ph, a, st);
+                default: return launch_impl<float, 4, 2, 8>(g, ph, a, st);
+            }
         default: return cudaErrorNotSupported;
     }
 }
@@ -369,8 +375,8 @@ cudaError_t launch_step_fused<double>(const Geometry<double> &g, const Physics<d
                                       int nstages, cudaStream_t st) {
     if (a.classical && nstages == 4) return cudaErrorNotSupported;
     switch (nstages) {
-        case 1: return launch_impl<double, 1, 1>(g, ph, a, st);
-        case 2: return launch_impl<double, 2, 1>(g, ph, a, st);
+        case 1: return launch_impl<double, 1, 1, 16>(g, ph, a, st);
+        case 2: return launch_impl<double, 2, 1, 12>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
 }
