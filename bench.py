@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the weather-sim time-stepping hot path on B200 (contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--kernel auto|stage_direct|step_fused]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--kernel auto|stage_direct|step_fused_reg|step_fused_tma]
 
 Metric (BASELINE.json): grid cell-updates/s of the RK4 Shallow-Water step. A "step" is one full RK4 time
 step over the whole grid. N = 1 runs BASELINE config 2 (SWE 8192x8192 fp32 RK4); N > 1 is weak scaling with
@@ -243,7 +243,7 @@ def run_b200_arm(args, rank, world, local_rank):
         peak, peak_kind = measured_peaks()
         kernel = sim.kernel_name
         launches_per_step = launches / max(args.steps, 1)
-        bpc = BYTES_PER_CELL_STEP_FUSED if kernel == "step_fused" else BYTES_PER_CELL_STEP_4PASS
+        bpc = BYTES_PER_CELL_STEP_FUSED if kernel.startswith("step_fused") else BYTES_PER_CELL_STEP_4PASS
         cells_rank = GRID_W * nrows
         achieved = bpc * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9
         roofline = {
@@ -254,7 +254,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "equivalent_4pass_gbs": BYTES_PER_CELL_STEP_4PASS * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9,
             "note": ("step_fused keeps all four RK stages in registers: it moves 24 B/cell-step instead of the "
                      "168 B/cell-step of the one-pass-per-stage design and is bound by fp32 issue (no FMA allowed "
-                     "for bit parity), see DESIGN.md") if kernel == "step_fused" else
+                     "for bit parity), see DESIGN.md") if kernel.startswith("step_fused") else
                     "one fused tendency+update pass per RK stage (4 launches per step), 168 B/cell-step",
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
@@ -303,7 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "stage_direct", "step_fused"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "stage_direct", "step_fused_reg", "step_fused_tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()

@@ -82,10 +82,12 @@ typedef enum wsb_rk4_mode {
 
 /* Which hand-written sm_100a path advances the state. All variants produce bit-identical results. */
 typedef enum wsb_kernel_variant {
-    WSB_KERNEL_AUTO = 0,       /* best available for the configuration */
-    WSB_KERNEL_STAGE_DIRECT = 1, /* one fused tendency+update pass per RK stage, direct global loads */
-    WSB_KERNEL_STAGE_TMA = 2,    /* one pass per RK stage, TMA-staged 2-D tiles with halo in shared memory */
-    WSB_KERNEL_STEP_FUSED = 3    /* all RK stages of a step in ONE pass: register-resident row sweep, warp shuffles */
+    WSB_KERNEL_AUTO = 0,           /* best available for the configuration */
+    WSB_KERNEL_STAGE_DIRECT = 1,   /* one fused tendency+update pass per RK stage, direct global loads */
+    WSB_KERNEL_STEP_FUSED_REG = 2, /* all RK stages of a step in ONE pass: register-resident row sweep, warp
+                                      shuffles, y rows prefetched into registers with 64-bit global loads */
+    WSB_KERNEL_STEP_FUSED_TMA = 3  /* same sweep; y rows staged by TMA bulk copies (cp.async.bulk + mbarrier) into
+                                      a per-warp shared-memory ring, k2/k3 windows in shared memory */
 } wsb_kernel_variant;
 
 /* ------------------------------------------------------------- structs -- */

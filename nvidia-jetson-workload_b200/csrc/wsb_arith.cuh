@@ -71,3 +71,79 @@ __device__ __forceinline__ T rk4_combine(T y, T dt6, T k1, T k2, T k3, T k4) {
 }
 
 }  // namespace wsb
+
+// ---- packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2, two IEEE operations per issue slot) -----------
+// ptxas 12.9 contracts a packed multiply feeding a packed add/sub into FFMA2 even for mul.rn/add.rn and
+// even under --fmad=false, which would break bit parity. The rule used here therefore is:
+// every add/sub that consumes a product is issued as two SCALAR add.rn.f32 (never contracted), while
+// multiplies and the adds/subs of non-products are packed. The build checks that the RECIP kernels
+// contain no FFMA/FFMA2 at all (profiles/check_no_fma.sh).
+namespace wsb {
+
+struct F2 {
+    float x, y;
+};
+
+__device__ __forceinline__ unsigned long long f2_pack(F2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ F2 f2_unpack(unsigned long long v) {
+    F2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_splat(float v) { return F2{v, v}; }
+// packed: products, and sums/differences whose operands are not products
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ F2 f2_sub_packed(F2 a, F2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ F2 f2_add_packed(F2 a, F2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+// scalar pairs: for sums/differences that consume a product
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { return F2{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) { return F2{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
+__device__ __forceinline__ F2 f2_neg(F2 a) { return F2{-a.x, -a.y}; }
+
+// Constants of the packed path, splatted once per kernel.
+struct PhysicsF2 {
+    F2 rdx, rdy, g, f;
+};
+
+// tendency_cell for a pair of horizontally adjacent cells, exact-reciprocal spacing only. Same operation
+// order as tendency_cell<float, true>: results are bit-identical.
+__device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F2 h, F2 uL, F2 uR, F2 uU, F2 uD, F2 vL,
+                                              F2 vR, F2 vU, F2 vD, F2 hL, F2 hR, F2 hU, F2 hD, F2 &du, F2 &dv, F2 &dh) {
+    const F2 ux = f2_mul(f2_sub_packed(uR, uL), ph.rdx);
+    const F2 uy = f2_mul(f2_sub_packed(uD, uU), ph.rdy);
+    const F2 vx = f2_mul(f2_sub_packed(vR, vL), ph.rdx);
+    const F2 vy = f2_mul(f2_sub_packed(vD, vU), ph.rdy);
+    const F2 hx = f2_mul(f2_sub_packed(hR, hL), ph.rdx);
+    const F2 hy = f2_mul(f2_sub_packed(hD, hU), ph.rdy);
+    // ((((-u)*ux) - (v*uy)) - (g*hx)) + (f*v); (-u)*ux == -(u*ux) exactly
+    du = f2_add(f2_sub(f2_sub(f2_neg(f2_mul(u, ux)), f2_mul(v, uy)), f2_mul(ph.g, hx)), f2_mul(ph.f, v));
+    dv = f2_sub(f2_sub(f2_sub(f2_neg(f2_mul(u, vx)), f2_mul(v, vy)), f2_mul(ph.g, hy)), f2_mul(ph.f, u));
+    dh = f2_sub(f2_sub(f2_neg(f2_mul(h, f2_add(ux, vy))), f2_mul(u, hx)), f2_mul(v, hy));
+}
+
+__device__ __forceinline__ F2 axpy_pair(F2 y, F2 c, F2 k) { return f2_add(y, f2_mul(c, k)); }
+
+// y + dt6 * (((k1 + 2*k2) + 2*k3) + k4)
+__device__ __forceinline__ F2 rk4_combine_pair(F2 y, F2 dt6, F2 k1, F2 k2, F2 k3, F2 k4) {
+    const F2 two = f2_splat(2.0f);
+    const F2 s = f2_add_packed(f2_add(f2_add(k1, f2_mul(two, k2)), f2_mul(two, k3)), k4);
+    return f2_add(y, f2_mul(dt6, s));
+}
+
+}  // namespace wsb

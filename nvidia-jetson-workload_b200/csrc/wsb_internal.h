@@ -15,6 +15,11 @@ namespace wsb {
 // Ghost rows kept above and below every field so that a row slab can hold its neighbours' rows:
 // 1 per RK stage, 4 for a whole fused RK4 step.
 constexpr int kHaloRows = 4;
+// One more never-written guard row on each side: the TMA-staged kernel copies whole 256-byte strip rows
+// that may start up to 16 bytes before a row and end up to 240 bytes past it (columns outside the
+// domain, whose values are never used), so the first/last ghost row needs slack inside the allocation.
+constexpr int kGuardRows = 1;
+constexpr int kLeadRows = kHaloRows + kGuardRows;  // rows between the allocation start and local row 0
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_last_error(const std::string &msg);
@@ -117,6 +122,12 @@ template <typename T>
 cudaError_t launch_step_fused(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
                               cudaStream_t st);
 bool step_fused_supported(int nstages, int dtype);
+
+// whole-step fused path with TMA-staged y rows (wsb_step_tma.cu)
+template <typename T>
+cudaError_t launch_step_tma(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
+                            cudaStream_t st);
+bool step_tma_supported(int nstages, int dtype);
 
 // ---- NCCL, loaded lazily with dlopen (wsb_nccl.cpp) -------------------------------------------
 struct NcclApi;

@@ -76,7 +76,7 @@ struct wsb_grid {
     // pointer to (level 0, local row 0, x 0)
     void *origin(int field) const {
         if (!f[field].base) return nullptr;
-        return (char *)f[field].base + (size_t)kHaloRows * pitch * elem_size(dtype);
+        return (char *)f[field].base + (size_t)kLeadRows * pitch * elem_size(dtype);
     }
     template <typename T>
     Geometry<T> geom() const {
@@ -109,7 +109,7 @@ static int grid_alloc_plane(wsb_grid *g, void **out) {
 }
 
 static int grid_fill(wsb_grid *g, void *base, double value) {
-    void *origin = (char *)base + (size_t)kHaloRows * g->pitch * elem_size(g->dtype);
+    void *origin = (char *)base + (size_t)kLeadRows * g->pitch * elem_size(g->dtype);
     if (g->dtype == WSB_F64) WSB_CUDA(launch_fill<double>(g->geom<double>(), (double *)origin, value, true, g->stream));
     else WSB_CUDA(launch_fill<float>(g->geom<float>(), (float *)origin, (float)value, true, g->stream));
     return WSB_OK;
@@ -149,7 +149,7 @@ static int grid_init(wsb_grid *g, int W, int H, int L, double dx, double dy, int
     g->dy = dtype == WSB_F32 ? (double)(float)dy : dy;
     const int align = 128 / (int)elem_size(dtype);  // rows start on 128-byte boundaries
     g->pitch = (W + align - 1) / align * align;
-    g->level_stride = (long long)(H + 2 * kHaloRows) * g->pitch;
+    g->level_stride = (long long)(H + 2 * kLeadRows) * g->pitch;
     g->row0 = row0;
     g->Hglobal = Hglobal;
     WSB_CUDA(cudaSetDevice(device));
@@ -177,7 +177,8 @@ static void grid_fini(wsb_grid *g) {
 }
 
 // --------------------------------------------------------------------------------------- sim --
-enum KernelPath { PATH_STAGE_DIRECT = 1, PATH_STAGE_TMA = 2, PATH_STEP_FUSED = 3 };
+enum KernelPath { PATH_STAGE_DIRECT = 1, PATH_STEP_REG = 2, PATH_STEP_TMA = 3 };
+static inline bool is_step_path(int p) { return p == PATH_STEP_REG || p == PATH_STEP_TMA; }
 
 struct wsb_sim {
     wsb_config cfg{};
@@ -211,7 +212,7 @@ struct wsb_sim {
 };
 
 static void *plane_origin(const wsb_sim *s, void *base) {
-    return base ? (char *)base + (size_t)kHaloRows * s->cur.pitch * elem_size(s->dtype) : nullptr;
+    return base ? (char *)base + (size_t)kLeadRows * s->cur.pitch * elem_size(s->dtype) : nullptr;
 }
 
 static int sim_alloc3(wsb_sim *s, void *dst[3]) {
@@ -339,6 +340,12 @@ static int enqueue_step_stages(wsb_sim *s) {
 }
 
 template <typename T>
+static cudaError_t launch_step(const wsb_sim *s, const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a) {
+    return s->path == PATH_STEP_TMA ? launch_step_tma<T>(g, ph, a, s->nstages, s->stream)
+                                    : launch_step_fused<T>(g, ph, a, s->nstages, s->stream);
+}
+
+template <typename T>
 static int enqueue_step_fused(wsb_sim *s) {
     const Geometry<T> g = s->cur.geom<T>();
     const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
@@ -354,25 +361,25 @@ static int enqueue_step_fused(wsb_sim *s) {
     const int halo = s->nstages;  // one ghost row per fused stage
     if (!s->comm) {
         a.y_begin = 0; a.y_end = H;
-        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        WSB_CUDA(launch_step<T>(s, g, ph, a));
         s->metrics.kernel_launches += 1;
         return WSB_OK;
     }
     WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
     const int e = std::min(halo, H);
     a.y_begin = 0; a.y_end = e;
-    WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+    WSB_CUDA(launch_step<T>(s, g, ph, a));
     s->metrics.kernel_launches += 1;
     if (H > e) {
         a.y_begin = std::max(e, H - halo); a.y_end = H;
-        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        WSB_CUDA(launch_step<T>(s, g, ph, a));
         s->metrics.kernel_launches += 1;
     }
     WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
     WSB_TRY(sim_exchange(s, s->next, halo, s->ev_edge));
     if (H > 2 * halo) {
         a.y_begin = halo; a.y_end = H - halo;
-        WSB_CUDA(launch_step_fused<T>(g, ph, a, s->nstages, s->stream));
+        WSB_CUDA(launch_step<T>(s, g, ph, a));
         s->metrics.kernel_launches += 1;
     }
     return WSB_OK;
@@ -402,7 +409,7 @@ static int sim_ensure_halo(wsb_sim *s) {
     if (!s->comm || s->halo_valid) return WSB_OK;
     void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
     WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
-    const int depth = s->path == PATH_STEP_FUSED ? s->nstages : 1;
+    const int depth = is_step_path(s->path) ? s->nstages : 1;
     WSB_TRY(sim_exchange(s, cur3, depth, s->ev_edge));
     s->halo_valid = true;
     return WSB_OK;
@@ -411,7 +418,7 @@ static int sim_ensure_halo(wsb_sim *s) {
 // one step, enqueued (weather_simulation.cpp:117-158 without the host-side bookkeeping)
 static int sim_enqueue_step(wsb_sim *s) {
     WSB_TRY(sim_ensure_halo(s));
-    if (s->path == PATH_STEP_FUSED) {
+    if (is_step_path(s->path)) {
         if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_fused<double>(s));
         else WSB_TRY(enqueue_step_fused<float>(s));
     } else {
@@ -817,34 +824,32 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             if (cudaEventCreate(e) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
         if (st != WSB_OK) break;
 
-        // kernel path
+        // kernel path. The whole-step kernels implement the reference (aliased) RK4 combine only.
         int want = c.kernel_variant;
-        // the whole-step kernel implements the reference (aliased) RK4 combine only
-        const bool fused_ok = step_fused_supported(s->nstages, s->dtype) &&
-                              !(s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL);
-        if (want == WSB_KERNEL_AUTO) want = fused_ok ? WSB_KERNEL_STEP_FUSED : WSB_KERNEL_STAGE_DIRECT;
-        if (want == WSB_KERNEL_STEP_FUSED) {
-            if (!fused_ok) {
+        const bool classical4 = s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL;
+        const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4;
+        const bool tma_ok = step_tma_supported(s->nstages, s->dtype) && !classical4;
+        if (want == WSB_KERNEL_AUTO)
+            want = tma_ok ? WSB_KERNEL_STEP_FUSED_TMA : reg_ok ? WSB_KERNEL_STEP_FUSED_REG : WSB_KERNEL_STAGE_DIRECT;
+        if (want == WSB_KERNEL_STEP_FUSED_REG || want == WSB_KERNEL_STEP_FUSED_TMA) {
+            if (!(want == WSB_KERNEL_STEP_FUSED_REG ? reg_ok : tma_ok)) {
                 st = fail(WSB_ERR_INVALID_ARGUMENT, "kernel_variant STEP_FUSED is not available for this configuration");
                 break;
             }
-            s->path = PATH_STEP_FUSED;
-        } else if (want == WSB_KERNEL_STAGE_TMA) {
-            st = fail(WSB_ERR_INVALID_ARGUMENT, "kernel_variant STAGE_TMA is not built into this library");
-            break;
+            s->path = want == WSB_KERNEL_STEP_FUSED_REG ? PATH_STEP_REG : PATH_STEP_TMA;
         } else if (want == WSB_KERNEL_STAGE_DIRECT) {
             s->path = PATH_STAGE_DIRECT;
         } else {
             st = fail(WSB_ERR_INVALID_ARGUMENT, "unknown kernel_variant");
             break;
         }
-        if (s->nrows < (s->path == PATH_STEP_FUSED ? s->nstages : 1) && c.nranks > 1) {
+        if (s->nrows < (is_step_path(s->path) ? s->nstages : 1) && c.nranks > 1) {
             st = fail(WSB_ERR_INVALID_ARGUMENT, "row slab thinner than the ghost depth");
             break;
         }
 
         if ((st = sim_alloc3(s, s->next)) != WSB_OK) break;
-        if (s->path != PATH_STEP_FUSED) {
+        if (!is_step_path(s->path)) {
             if (s->nstages >= 2 && (st = sim_alloc3(s, s->tA)) != WSB_OK) break;
             if (s->nstages == 4) {
                 if ((st = sim_alloc3(s, s->tB)) != WSB_OK) break;
@@ -999,8 +1004,8 @@ int wsb_sim_local_rows(const wsb_sim *s, int32_t *row0, int32_t *nrows) {
 const char *wsb_sim_kernel_name(const wsb_sim *s) {
     if (!s) return "";
     switch (s->path) {
-        case PATH_STEP_FUSED: return "step_fused";
-        case PATH_STAGE_TMA: return "stage_tma";
+        case PATH_STEP_REG: return "step_fused_reg";
+        case PATH_STEP_TMA: return "step_fused_tma";
         default: return "stage_direct";
     }
 }

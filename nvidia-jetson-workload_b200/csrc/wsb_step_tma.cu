@@ -1,0 +1,478 @@
+// Whole-step fused kernel, TMA-staged variant (sm_100a): ALL Runge-Kutta stages of one time step in ONE
+// pass over the grid, like wsb_step_fused.cu, but the rows of y_n are brought on chip by the TMA engine.
+//
+//   * each warp owns a strip of 32*V columns and sweeps down the rows with the same time skew as the
+//     register variant (stage s works on row n-s when row n of y arrives);
+//   * y rows land in a per-warp shared-memory ring of kRing rows through cp.async.bulk (global -> shared,
+//     SASS UBLKCP) completing on one mbarrier per ring slot; lane 0 is the producer: it re-arms a slot
+//     as soon as its row is dead, so (kRing - S - 1) rows are always in flight and HBM latency is hidden
+//     without spending registers on prefetch;
+//   * y is re-read from the ring wherever a stage needs it (stencil rows of stage 1, base rows y + c*k),
+//     the k2/k3 rows the RK4 combine needs later are parked in shared memory too (private per lane, no
+//     synchronisation), and only the 3-row windows of the intermediate stage states stay in registers:
+//     ~110 registers instead of ~170, i.e. 16 instead of 12 resident warps per SM, and a 3x instead of 6x
+//     unrolled loop body that fits the instruction cache;
+//   * a steady-state fast path (interior strip, pipeline full, no domain edge in reach) runs without a
+//     single boundary test; the general path is the register variant's logic.
+//
+// Arithmetic per cell is wsb_arith.cuh: bit-identical to every other path and to the CPU oracle.
+#include "wsb_arith.cuh"
+#include "wsb_internal.h"
+
+#include <cstdint>
+#include <cstdlib>
+#include <type_traits>
+
+namespace wsb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRing = 8;  // y rows resident per warp (power of two)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WSB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WSB_DONE;\n"
+        "bra WSB_WAIT;\n"
+        "WSB_DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <typename T, int V>
+struct Row {
+    T f[3][V];
+};
+
+template <typename T, int V>
+struct SmemIO;
+template <>
+struct SmemIO<float, 2> {
+    static __device__ __forceinline__ void ld(const float *p, float (&r)[2]) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        r[0] = t.x; r[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float *p, const float (&r)[2]) {
+        *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]);
+    }
+};
+template <>
+struct SmemIO<double, 1> {
+    static __device__ __forceinline__ void ld(const double *p, double (&r)[1]) { r[0] = *p; }
+    static __device__ __forceinline__ void st(double *p, const double (&r)[1]) { *p = r[0]; }
+};
+
+template <typename T, int NST, int V>
+struct Layout {
+    static constexpr int SW = 32 * V;                                   // strip width in columns
+    static constexpr int ALIGN = 16 / (int)sizeof(T);                   // TMA needs 16-byte aligned rows
+    static constexpr int HX = (NST + ALIGN - 1) / ALIGN * ALIGN;        // halo columns per side
+    static constexpr int OUTW = SW - 2 * HX;                            // output columns per strip
+    static constexpr int FIELD_BYTES = SW * (int)sizeof(T);
+    static constexpr int ROW_ELEMS = 3 * SW;
+    static constexpr int ROW_BYTES = 3 * FIELD_BYTES;
+    static constexpr int K_ROWS = NST == 4 ? 5 : 0;                     // k2: 3 rows, k3: 2 rows
+    static constexpr int SMEM_BYTES = (kRing + K_ROWS) * ROW_BYTES + kRing * 8;
+};
+
+template <typename T, int NST, int V, bool RECIP>
+struct SweepT {
+    using L = Layout<T, NST, V>;
+
+    const Geometry<T> &g;
+    const Physics<T> &ph;
+    const StepArgs<T> &a;
+    PhysicsF2 ph2;  // splatted constants of the packed path
+    int lane, c0, xs;
+    bool edge_strip, fix_left, fix_right;
+    int y0, niter, gmin, gmax, out_lo, out_hi;
+    long long lvl_off;
+    T *ring;        // [kRing][3][SW]
+    T *k2s;         // [3][3][SW]
+    T *k3s;         // [2][3][SW]
+    uint32_t ring_u32, bar_u32;
+    bool st_vec, st_e[V], ragged;
+
+    __device__ __forceinline__ SweepT(const Geometry<T> &g_, const Physics<T> &ph_, const StepArgs<T> &a_)
+        : g(g_), ph(ph_), a(a_) {}
+
+    // ---- producer side (lane 0) -------------------------------------------------------------------
+    __device__ __forceinline__ void issue_row(int m) const {
+        int r = y0 - NST + m;
+        r = max(r, gmin);
+        r = min(r, gmax - 1);  // clamp-to-self rows of the reference (weather_simulation.cpp:512-513)
+        const long long off = lvl_off + (long long)r * g.pitch + xs;
+        const int slot = m & (kRing - 1);
+        const uint32_t bar = bar_u32 + 8u * slot;
+        const uint32_t dst = ring_u32 + (uint32_t)slot * L::ROW_BYTES;
+        mbar_expect_tx(bar, L::ROW_BYTES);
+        bulk_g2s(dst, a.Y.u + off, L::FIELD_BYTES, bar);
+        bulk_g2s(dst + L::FIELD_BYTES, a.Y.v + off, L::FIELD_BYTES, bar);
+        bulk_g2s(dst + 2 * L::FIELD_BYTES, a.Y.h + off, L::FIELD_BYTES, bar);
+    }
+
+    // ---- consumer side ------------------------------------------------------------------------------
+    __device__ __forceinline__ void wait_row(int m) const {
+        const int slot = m & (kRing - 1);
+        mbar_wait(bar_u32 + 8u * slot, (uint32_t)(m / kRing) & 1u);
+        if (edge_strip) {
+            // clamp-to-self columns (weather_simulation.cpp:510-511): column -1 := column 0, column W := column W-1
+            if (lane == 0) {
+                T *row = ring + slot * L::ROW_ELEMS;
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    if (fix_left) row[f * L::SW + L::HX - 1] = row[f * L::SW + L::HX];
+                    if (fix_right) row[f * L::SW + (g.W - xs)] = row[f * L::SW + (g.W - xs) - 1];
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    __device__ __forceinline__ void ld_ring(Row<T, V> &dst, int m) const {
+        const T *row = ring + (m & (kRing - 1)) * L::ROW_ELEMS + lane * V;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(row + f * L::SW, dst.f[f]);
+    }
+    __device__ __forceinline__ void ld_k(Row<T, V> &dst, const T *base, int slot) const {
+        const T *row = base + slot * L::ROW_ELEMS + lane * V;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(row + f * L::SW, dst.f[f]);
+    }
+    __device__ __forceinline__ void st_k(const Row<T, V> &src, T *base, int slot) const {
+        T *row = base + slot * L::ROW_ELEMS + lane * V;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) SmemIO<T, V>::st(row + f * L::SW, src.f[f]);
+    }
+
+    __device__ __forceinline__ void fix_columns(Row<T, V> &r) const {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const T from_right = __shfl_down_sync(kFull, r.f[f][0], 1);
+            const T from_left = __shfl_up_sync(kFull, r.f[f][V - 1], 1);
+            if (c0 + V - 1 == -1) r.f[f][V - 1] = from_right;           // column -1 := column 0
+            if (c0 == g.W) r.f[f][0] = from_left;                       // column W := column W-1
+            if (V == 2 && c0 + 1 == g.W) r.f[f][V - 1] = r.f[f][0];
+        }
+    }
+
+    // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
+    static constexpr bool kPacked = std::is_same<T, float>::value && V == 2 && RECIP;
+
+    __device__ __forceinline__ void tendency_row(const Row<T, V> &U, const Row<T, V> &C, const Row<T, V> &D,
+                                                 Row<T, V> &k) const {
+        T Lft[3], Rgt[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            Lft[f] = __shfl_up_sync(kFull, C.f[f][V - 1], 1);
+            Rgt[f] = __shfl_down_sync(kFull, C.f[f][0], 1);
+        }
+        if constexpr (kPacked) {
+            auto P = [](const T(&r)[V]) { return F2{(float)r[0], (float)r[1]}; };
+            F2 du, dv, dh;
+            tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]),
+                          F2{(float)Lft[0], (float)C.f[0][0]}, F2{(float)C.f[0][1], (float)Rgt[0]}, P(U.f[0]), P(D.f[0]),
+                          F2{(float)Lft[1], (float)C.f[1][0]}, F2{(float)C.f[1][1], (float)Rgt[1]}, P(U.f[1]), P(D.f[1]),
+                          F2{(float)Lft[2], (float)C.f[2][0]}, F2{(float)C.f[2][1], (float)Rgt[2]}, P(U.f[2]), P(D.f[2]),
+                          du, dv, dh);
+            k.f[0][0] = du.x; k.f[0][1] = du.y;
+            k.f[1][0] = dv.x; k.f[1][1] = dv.y;
+            k.f[2][0] = dh.x; k.f[2][1] = dh.y;
+            return;
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const T uL = (e == 0) ? Lft[0] : C.f[0][e - 1], uR = (e == V - 1) ? Rgt[0] : C.f[0][e + 1];
+            const T vL = (e == 0) ? Lft[1] : C.f[1][e - 1], vR = (e == V - 1) ? Rgt[1] : C.f[1][e + 1];
+            const T hL = (e == 0) ? Lft[2] : C.f[2][e - 1], hR = (e == V - 1) ? Rgt[2] : C.f[2][e + 1];
+            tendency_cell<T, RECIP>(ph, C.f[0][e], C.f[1][e], C.f[2][e], uL, uR, U.f[0][e], D.f[0][e], vL, vR,
+                                    U.f[1][e], D.f[1][e], hL, hR, U.f[2][e], D.f[2][e], k.f[0][e], k.f[1][e],
+                                    k.f[2][e]);
+        }
+    }
+
+    __device__ __forceinline__ void store_out(const Row<T, V> &o, int r) const {
+        const long long off = lvl_off + (long long)r * g.pitch + c0;
+        if (!ragged) {  // block-uniform: every lane is entirely inside or entirely outside the output range
+            if (st_vec) {
+                SmemIO<T, V>::st(a.O.u + off, o.f[0]);  // plain vector store (generic address)
+                SmemIO<T, V>::st(a.O.v + off, o.f[1]);
+                SmemIO<T, V>::st(a.O.h + off, o.f[2]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if (st_e[e]) {
+                    a.O.u[off + e] = o.f[0][e];
+                    a.O.v[off + e] = o.f[1][e];
+                    a.O.h[off + e] = o.f[2][e];
+                }
+        }
+    }
+
+    // Stage S1 (1-based) at iteration n; PH = n % 3. Center row index m = n - S1.
+    template <int PH, int S1, bool FAST>
+    __device__ __forceinline__ void stage(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
+        constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
+        const int r = y0 - NST + n - S1;
+        if (!FAST) {
+            if (n < 2 * S1) return;  // pipeline fill
+            if (r < gmin) return;
+            if (r >= gmax) {
+                if constexpr (S1 < NST) {
+                    if (r == gmax) {  // one past the bottom edge: "down" of the last row is the last row
+                        asm volatile("");
+                        Lv[S1 - 1][m3] = Lv[S1 - 1][m3m];
+                    }
+                }
+                return;
+            }
+        }
+        Row<T, V> k, yb;
+        if constexpr (S1 == 1) {
+            Row<T, V> U, D;
+            ld_ring(U, n - 2);
+            ld_ring(yb, n - 1);
+            ld_ring(D, n);
+            tendency_row(U, yb, D, k);
+        } else {
+            tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k);
+            ld_ring(yb, n - S1);
+        }
+        if constexpr (S1 < NST) {
+            const T c = (NST == 4 && S1 == 3) ? a.dt : a.half_dt;
+            Row<T, V> &t = Lv[S1 - 1][m3];
+            if constexpr (kPacked) {
+                const F2 c2 = f2_splat((float)c);
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    const F2 r = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, c2,
+                                           F2{(float)k.f[f][0], (float)k.f[f][1]});
+                    t.f[f][0] = r.x; t.f[f][1] = r.y;
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < 3; ++f)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) t.f[f][e] = axpy<T>(yb.f[f][e], c, k.f[f][e]);
+            }
+            if (!FAST) {
+                if (edge_strip) fix_columns(t);
+                if (r == gmin) {  // row -1 := row 0 ("up" of the first row)
+                    asm volatile("");
+                    Lv[S1 - 1][m3m] = t;
+                }
+            }
+            if constexpr (NST == 4 && S1 == 2) st_k(k, k2s, m3);
+            if constexpr (NST == 4 && S1 == 3) st_k(k, k3s, (n - S1) & 1);
+        } else {
+            Row<T, V> o;
+            if constexpr (NST == 4) {
+                Row<T, V> k2, k3;
+                ld_k(k2, k2s, m3);
+                ld_k(k3, k3s, (n - S1) & 1);
+                // reference aliasing: "k1" reads k4 at the combine (weather_simulation.cpp:350-351, F5)
+                if constexpr (kPacked) {
+                    const F2 dt6 = f2_splat((float)a.dt6);
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) {
+                        const F2 k4 = F2{(float)k.f[f][0], (float)k.f[f][1]};
+                        const F2 r = rk4_combine_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt6, k4,
+                                                      F2{(float)k2.f[f][0], (float)k2.f[f][1]},
+                                                      F2{(float)k3.f[f][0], (float)k3.f[f][1]}, k4);
+                        o.f[f][0] = r.x; o.f[f][1] = r.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 3; ++f)
+#pragma unroll
+                        for (int e = 0; e < V; ++e)
+                            o.f[f][e] = rk4_combine<T>(yb.f[f][e], a.dt6, k.f[f][e], k2.f[f][e], k3.f[f][e], k.f[f][e]);
+                }
+            } else if constexpr (kPacked) {
+                const F2 dt2 = f2_splat((float)a.dt);
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    const F2 r = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt2,
+                                           F2{(float)k.f[f][0], (float)k.f[f][1]});
+                    o.f[f][0] = r.x; o.f[f][1] = r.y;
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < 3; ++f)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) o.f[f][e] = axpy<T>(yb.f[f][e], a.dt, k.f[f][e]);
+            }
+            store_out(o, r);
+        }
+    }
+
+    template <int PH, bool FAST>
+    __device__ __forceinline__ void stages(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
+        stage<PH, 1, FAST>(Lv, n);
+        if constexpr (NST >= 2) stage<PH, 2, FAST>(Lv, n);
+        if constexpr (NST >= 4) {
+            stage<PH, 3, FAST>(Lv, n);
+            stage<PH, 4, FAST>(Lv, n);
+        }
+    }
+
+    template <int PH>
+    __device__ __forceinline__ void iteration(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
+        wait_row(n);
+        const int r_last = y0 - NST + n - NST;  // center row of the final stage (smallest row touched)
+        const int r_first = y0 - NST + n - 1;   // center row of stage 1 (largest)
+        const bool fast = !edge_strip && n >= 2 * NST && r_last > gmin && r_first < gmax;
+        if (fast) stages<PH, true>(Lv, n);
+        else stages<PH, false>(Lv, n);
+        __syncwarp();
+        // the oldest row is dead now: re-arm its slot with the row kRing ahead
+        constexpr int KEEP = NST > 2 ? NST : 2;
+        const int dead = n - KEEP;
+        // (generic-proxy reads of the slot are complete: their values were consumed before the __syncwarp)
+        if (lane == 0 && dead >= 0 && dead + kRing < niter) issue_row(dead + kRing);
+    }
+
+    __device__ __forceinline__ void run() const {
+        Row<T, V> Lv[(NST > 1 ? NST - 1 : 1)][3];
+        int n = 0;
+        for (; n + 3 <= niter; n += 3) {
+            iteration<0>(Lv, n);
+            iteration<1>(Lv, n + 1);
+            iteration<2>(Lv, n + 2);
+        }
+        if (n < niter) iteration<0>(Lv, n);
+        if (n + 1 < niter) iteration<1>(Lv, n + 1);
+    }
+};
+
+template <typename T, int NST, int V, bool RECIP, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+    step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk) {
+    using L = Layout<T, NST, V>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int strip = blockIdx.x;
+    const int y0 = a.y_begin + blockIdx.y * rows_per_chunk;
+    const int y1 = min(y0 + rows_per_chunk, a.y_end);
+    if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform
+
+    SweepT<T, NST, V, RECIP> sw(g, ph, a);
+    sw.ph2.rdx = f2_splat((float)ph.rdx);
+    sw.ph2.rdy = f2_splat((float)ph.rdy);
+    sw.ph2.g = f2_splat((float)ph.g);
+    sw.ph2.f = f2_splat((float)ph.f);
+    sw.lane = lane;
+    sw.xs = strip * L::OUTW - L::HX;
+    sw.c0 = sw.xs + lane * V;
+    sw.fix_left = sw.xs < 0;
+    sw.fix_right = sw.xs + L::SW > g.W;
+    sw.edge_strip = sw.fix_left || sw.fix_right;
+    sw.y0 = y0;
+    sw.niter = (y1 - y0) + 2 * NST;
+    sw.gmin = -g.row0;
+    sw.gmax = g.Hglobal - g.row0;
+    sw.out_lo = strip * L::OUTW;
+    sw.out_hi = min(sw.out_lo + L::OUTW, g.W);
+    sw.lvl_off = (long long)blockIdx.z * g.level_stride;
+    sw.ring = reinterpret_cast<T *>(smem_raw);
+    sw.k2s = sw.ring + kRing * L::ROW_ELEMS;
+    sw.k3s = sw.k2s + 3 * L::ROW_ELEMS;
+    sw.ring_u32 = smem_u32(sw.ring);
+    sw.bar_u32 = smem_u32(smem_raw + (kRing + L::K_ROWS) * L::ROW_BYTES);
+    bool all_in = true;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        sw.st_e[e] = (sw.c0 + e >= sw.out_lo) && (sw.c0 + e < sw.out_hi);
+        all_in = all_in && sw.st_e[e];
+    }
+    sw.st_vec = all_in;
+    sw.ragged = V > 1 && ((sw.out_hi - sw.out_lo) % V != 0);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) mbar_init(sw.bar_u32 + 8u * s, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        const int pre = min(kRing, sw.niter);
+        for (int m = 0; m < pre; ++m) sw.issue_row(m);
+    }
+    __syncwarp();
+    sw.run();
+}
+
+int env_int(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+int rows_per_chunk_default() {
+    static const int v = env_int("WSB_FUSED_ROWS_PER_CHUNK", 128);
+    return v > 0 ? v : 128;
+}
+
+template <typename T, int NST, int V, int MINB>
+cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
+    using L = Layout<T, NST, V>;
+    const int rows = a.y_end - a.y_begin;
+    if (rows <= 0) return cudaSuccess;
+    const int strips = (g.W + L::OUTW - 1) / L::OUTW;
+    const int rpc = rows_per_chunk_default();
+    const dim3 grid(strips, (rows + rpc - 1) / rpc, g.L);
+    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
+    else step_tma_kernel<T, NST, V, false, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool step_tma_supported(int nstages, int dtype) {
+    if (dtype == WSB_F64) return nstages == 1 || nstages == 2;
+    return nstages == 1 || nstages == 2 || nstages == 4;
+}
+
+template <>
+cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float> &ph, const StepArgs<float> &a,
+                                   int nstages, cudaStream_t st) {
+    if (a.classical && nstages == 4) return cudaErrorNotSupported;
+    switch (nstages) {
+        case 1: return launch_impl<float, 1, 2, 20>(g, ph, a, st);
+        case 2: return launch_impl<float, 2, 2, 16>(g, ph, a, st);
+        case 4: return launch_impl<float, 4, 2, 16>(g, ph, a, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+template <>
+cudaError_t launch_step_tma<double>(const Geometry<double> &g, const Physics<double> &ph, const StepArgs<double> &a,
+                                    int nstages, cudaStream_t st) {
+    if (a.classical && nstages == 4) return cudaErrorNotSupported;
+    switch (nstages) {
+        case 1: return launch_impl<double, 1, 1, 20>(g, ph, a, st);
+        case 2: return launch_impl<double, 2, 1, 16>(g, ph, a, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace wsb

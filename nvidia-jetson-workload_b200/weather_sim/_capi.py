@@ -24,7 +24,7 @@ MODEL = {"shallow_water": 0, "barotropic": 1, "primitive": 2, "general": 3}
 INTEGRATOR = {"euler": 0, "rk2": 1, "rk4": 2, "adams_bashforth": 3, "semi_implicit": 4}
 FIELD = {"u": 0, "v": 1, "h": 2, "height": 2, "p": 3, "pressure": 3, "t": 4, "temperature": 4, "q": 5,
          "humidity": 5, "vorticity": 6, "divergence": 7}
-KERNEL = {"auto": 0, "stage_direct": 1, "stage_tma": 2, "step_fused": 3}
+KERNEL = {"auto": 0, "stage_direct": 1, "step_fused_reg": 2, "step_fused_tma": 3, "step_fused": 3}
 
 
 class wsb_config(ctypes.Structure):

@@ -28,9 +28,7 @@ for a, t in ins:
         mm = re.search(r"BRA\s+0x([0-9a-f]+)", t)
         if mm:
             tgt = int(mm.group(1), 16)
-            if tgt < a and (best is None or a - tgt > best[1] - best[0]) and not any(
-                "WARPSYNC" in tt for aa, tt in ins if tgt <= aa <= a
-            ):
+            if tgt < a and (best is None or a - tgt > best[1] - best[0]):
                 best = (tgt, a)
 print("kernel instructions:", len(ins))
 if best:

@@ -70,7 +70,8 @@ def test_slab_decomposition_bit_identical(world):
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     cases = [
-        (300, 67, 2, "step_fused", 5, "float32"),
+        (300, 67, 2, "step_fused_tma", 5, "float32"),
+        (300, 67, 2, "step_fused_reg", 5, "float32"),
         (300, 67, 2, "stage_direct", 5, "float32"),
         (130, 41, 1, "step_fused", 4, "float32"),
         (130, 41, 0, "step_fused", 4, "float32"),

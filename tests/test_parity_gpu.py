@@ -15,7 +15,7 @@ from weather_sim import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 FIELDS = ("u", "v", "h", "p", "t", "q", "vorticity")
-VARIANTS = ("stage_direct", "step_fused")
+VARIANTS = ("stage_direct", "step_fused_reg", "step_fused_tma")
 MODELS = ("shallow_water", "barotropic", "primitive", "general")
 INTEGRATORS = ("euler", "rk2", "rk4", "adams_bashforth", "semi_implicit")
 
@@ -178,7 +178,7 @@ def test_fp64_vs_oracle(kernel, integ):
         ic = tuple(a.astype(np.float64) for a in syn.random_vorticity(W, H, dtype=np.float64))
         compare_with_oracle(W, H, 1, integ, kernel, 10, ic, dtype=np.float64, dx=0.9, dy=1.1, coriolis_f=0.1)
         # fp64 SWE RK4 (4 stages) has no whole-step fused kernel (register budget): "auto" picks the stage path
-        k = "auto" if (integ == 2 and kernel == "step_fused") else kernel
+        k = "auto" if (integ == 2 and kernel.startswith("step_fused")) else kernel
         compare_with_oracle(W, H, 0, integ, k, 10, ic, dtype=np.float64, coriolis_f=0.1)
 
 
@@ -346,8 +346,8 @@ def test_full_size_8192_step_fused_equals_stage_path_and_oracle_crops():
         res[kernel + "_me"] = s.mass_energy()
         s.close()
     for n in ("u", "v", "h"):
-        assert_bit_equal(res["step_fused"][n], res["stage_direct"][n], f"8192 {n}")
-    assert res["step_fused_me"] == res["stage_direct_me"]
+        assert_bit_equal(res["step_fused_tma"][n], res["stage_direct"][n], f"8192 {n}")
+    assert res["step_fused_tma_me"] == res["stage_direct_me"]
     C, R = 160, 8  # crop size, dependency radius of 2 RK4 steps
     windows = [(0, 0), (0, W - C), (H - C, 0), (H - C, W - C), (4000, 4400), (120, 3300)]
     for (y0, x0) in windows:
@@ -357,6 +357,6 @@ def test_full_size_8192_step_fused_equals_stage_path_and_oracle_crops():
         ys = slice(0 if y0 == 0 else R, C if y0 + C == H else C - R)
         xs = slice(0 if x0 == 0 else R, C if x0 + C == W else C - R)
         for n in ("u", "v", "h"):
-            full = res["step_fused"][n][y0:y0 + C, x0:x0 + C]
+            full = res["step_fused_tma"][n][y0:y0 + C, x0:x0 + C]
             assert_bit_equal(np.ascontiguousarray(full[ys, xs]), np.ascontiguousarray(o.get_field(n)[ys, xs]),
                              f"crop ({y0},{x0}) {n}")
