@@ -121,15 +121,21 @@ struct PhysicsF2 {
     F2 rdx, rdy, g, f;
 };
 
-// tendency_cell for a pair of horizontally adjacent cells, exact-reciprocal spacing only. Same operation
-// order as tendency_cell<float, true>: results are bit-identical.
-__device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F2 h, F2 uL, F2 uR, F2 uU, F2 uD, F2 vL,
-                                              F2 vR, F2 vU, F2 vD, F2 hL, F2 hR, F2 hU, F2 hD, F2 &du, F2 &dv, F2 &dh) {
-    const F2 ux = f2_mul(f2_sub_packed(uR, uL), ph.rdx);
+// tendency_cell for a pair of horizontally adjacent cells (x, y) = (cell 0, cell 1), exact-reciprocal
+// spacing only. uLft/uRgt... are the cells left of cell 0 and right of cell 1 (from the neighbouring lanes).
+// Same operation order as tendency_cell<float, true>: results are bit-identical.
+__device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F2 h, float uLft, float uRgt, F2 uU, F2 uD,
+                                              float vLft, float vRgt, F2 vU, F2 vD, float hLft, float hRgt, F2 hU,
+                                              F2 hD, F2 &du, F2 &dv, F2 &dh) {
+    // horizontal differences as scalar subtractions (no register pairing needed): R - L per cell
+    const F2 dux = F2{__fsub_rn(u.y, uLft), __fsub_rn(uRgt, u.x)};
+    const F2 dvx = F2{__fsub_rn(v.y, vLft), __fsub_rn(vRgt, v.x)};
+    const F2 dhx = F2{__fsub_rn(h.y, hLft), __fsub_rn(hRgt, h.x)};
+    const F2 ux = f2_mul(dux, ph.rdx);
     const F2 uy = f2_mul(f2_sub_packed(uD, uU), ph.rdy);
-    const F2 vx = f2_mul(f2_sub_packed(vR, vL), ph.rdx);
+    const F2 vx = f2_mul(dvx, ph.rdx);
     const F2 vy = f2_mul(f2_sub_packed(vD, vU), ph.rdy);
-    const F2 hx = f2_mul(f2_sub_packed(hR, hL), ph.rdx);
+    const F2 hx = f2_mul(dhx, ph.rdx);
     const F2 hy = f2_mul(f2_sub_packed(hD, hU), ph.rdy);
     // ((((-u)*ux) - (v*uy)) - (g*hx)) + (f*v); (-u)*ux == -(u*ux) exactly
     du = f2_add(f2_sub(f2_sub(f2_neg(f2_mul(u, ux)), f2_mul(v, uy)), f2_mul(ph.g, hx)), f2_mul(ph.f, v));

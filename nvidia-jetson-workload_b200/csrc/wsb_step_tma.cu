@@ -3,10 +3,10 @@
 //
 //   * each warp owns a strip of 32*V columns and sweeps down the rows with the same time skew as the
 //     register variant (stage s works on row n-s when row n of y arrives);
-//   * y rows land in a per-warp shared-memory ring of kRing rows through cp.async.bulk (global -> shared,
-//     SASS UBLKCP) completing on one mbarrier per ring slot; lane 0 is the producer: it re-arms a slot
-//     as soon as its row is dead, so (kRing - S - 1) rows are always in flight and HBM latency is hidden
-//     without spending registers on prefetch;
+//   * y rows land in a per-warp shared-memory ring (3 groups of 3 rows) through cp.async.bulk (global ->
+//     shared, SASS UBLKCP), one mbarrier per group; lane 0 is the producer: as soon as the rows of triple
+//     q-2 are dead it re-arms their group with the rows of triple q+1, so HBM latency is hidden without
+//     spending registers on prefetch;
 //   * y is re-read from the ring wherever a stage needs it (stencil rows of stage 1, base rows y + c*k),
 //     the k2/k3 rows the RK4 combine needs later are parked in shared memory too (private per lane, no
 //     synchronisation), and only the 3-row windows of the intermediate stage states stay in registers:
@@ -28,7 +28,8 @@ namespace wsb {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kRing = 8;  // y rows resident per warp (power of two)
+constexpr int kGroups = 3;          // the y ring is 3 groups of 3 rows; the row loop is unrolled by 3,
+constexpr int kRing = 3 * kGroups;  // so every shared-memory offset is a compile-time constant
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,13 +93,19 @@ struct Layout {
     static constexpr int FIELD_BYTES = SW * (int)sizeof(T);
     static constexpr int ROW_ELEMS = 3 * SW;
     static constexpr int ROW_BYTES = 3 * FIELD_BYTES;
-    static constexpr int K_ROWS = NST == 4 ? 5 : 0;                     // k2: 3 rows, k3: 2 rows
-    static constexpr int SMEM_BYTES = (kRing + K_ROWS) * ROW_BYTES + kRing * 8;
+    static constexpr int K_ROWS = NST == 4 ? 6 : 0;                     // k2 and k3: 3 rows each
+    static constexpr int SMEM_BYTES = (kRing + K_ROWS) * ROW_BYTES + kGroups * 8;
 };
 
 template <typename T, int NST, int V, bool RECIP>
 struct SweepT {
     using L = Layout<T, NST, V>;
+    using Windows = Row<T, V>[(NST > 1 ? NST - 1 : 1)][3];
+
+    // lane-offset shared-memory bases of the ring groups holding rows of triple q, q-1 and q-2
+    struct Groups {
+        const T *a, *b, *c;
+    };
 
     const Geometry<T> &g;
     const Physics<T> &ph;
@@ -109,59 +116,73 @@ struct SweepT {
     int y0, niter, gmin, gmax, out_lo, out_hi;
     long long lvl_off;
     T *ring;        // [kRing][3][SW]
-    T *k2s;         // [3][3][SW]
-    T *k3s;         // [2][3][SW]
+    T *k2s;         // [3][3][SW], lane-offset
+    T *k3s;         // [3][3][SW], lane-offset
     uint32_t ring_u32, bar_u32;
     bool st_vec, st_e[V], ragged;
+
+    // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
+    static constexpr bool kPacked = std::is_same<T, float>::value && V == 2 && RECIP;
 
     __device__ __forceinline__ SweepT(const Geometry<T> &g_, const Physics<T> &ph_, const StepArgs<T> &a_)
         : g(g_), ph(ph_), a(a_) {}
 
-    // ---- producer side (lane 0) -------------------------------------------------------------------
-    __device__ __forceinline__ void issue_row(int m) const {
-        int r = y0 - NST + m;
-        r = max(r, gmin);
-        r = min(r, gmax - 1);  // clamp-to-self rows of the reference (weather_simulation.cpp:512-513)
-        const long long off = lvl_off + (long long)r * g.pitch + xs;
-        const int slot = m & (kRing - 1);
-        const uint32_t bar = bar_u32 + 8u * slot;
-        const uint32_t dst = ring_u32 + (uint32_t)slot * L::ROW_BYTES;
-        mbar_expect_tx(bar, L::ROW_BYTES);
-        bulk_g2s(dst, a.Y.u + off, L::FIELD_BYTES, bar);
-        bulk_g2s(dst + L::FIELD_BYTES, a.Y.v + off, L::FIELD_BYTES, bar);
-        bulk_g2s(dst + 2 * L::FIELD_BYTES, a.Y.h + off, L::FIELD_BYTES, bar);
+    // ---- producer side (lane 0): one group = 3 consecutive rows, one mbarrier -------------------------
+    __device__ __forceinline__ void issue_group(int q) const {
+        const int m0 = 3 * q;
+        const int nr = min(3, niter - m0);
+        if (nr <= 0) return;
+        const int grp = q % kGroups;
+        const uint32_t bar = bar_u32 + 8u * grp;
+        mbar_expect_tx(bar, (uint32_t)nr * L::ROW_BYTES);
+        for (int i = 0; i < nr; ++i) {
+            int r = y0 - NST + m0 + i;
+            r = max(r, gmin);
+            r = min(r, gmax - 1);  // clamp-to-self rows of the reference (weather_simulation.cpp:512-513)
+            const long long off = lvl_off + (long long)r * g.pitch + xs;
+            const uint32_t dst = ring_u32 + (uint32_t)(grp * 3 + i) * L::ROW_BYTES;
+            bulk_g2s(dst, a.Y.u + off, L::FIELD_BYTES, bar);
+            bulk_g2s(dst + L::FIELD_BYTES, a.Y.v + off, L::FIELD_BYTES, bar);
+            bulk_g2s(dst + 2 * L::FIELD_BYTES, a.Y.h + off, L::FIELD_BYTES, bar);
+        }
     }
 
     // ---- consumer side ------------------------------------------------------------------------------
-    __device__ __forceinline__ void wait_row(int m) const {
-        const int slot = m & (kRing - 1);
-        mbar_wait(bar_u32 + 8u * slot, (uint32_t)(m / kRing) & 1u);
+    __device__ __forceinline__ void wait_group(int q) const {
+        const int grp = q % kGroups;
+        mbar_wait(bar_u32 + 8u * grp, (uint32_t)(q / kGroups) & 1u);
         if (edge_strip) {
             // clamp-to-self columns (weather_simulation.cpp:510-511): column -1 := column 0, column W := column W-1
             if (lane == 0) {
-                T *row = ring + slot * L::ROW_ELEMS;
+                const int nr = min(3, niter - 3 * q);
+                for (int i = 0; i < nr; ++i) {
+                    T *row = ring + (grp * 3 + i) * L::ROW_ELEMS;
 #pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    if (fix_left) row[f * L::SW + L::HX - 1] = row[f * L::SW + L::HX];
-                    if (fix_right) row[f * L::SW + (g.W - xs)] = row[f * L::SW + (g.W - xs) - 1];
+                    for (int f = 0; f < 3; ++f) {
+                        if (fix_left) row[f * L::SW + L::HX - 1] = row[f * L::SW + L::HX];
+                        if (fix_right) row[f * L::SW + (g.W - xs)] = row[f * L::SW + (g.W - xs) - 1];
+                    }
                 }
             }
             __syncwarp();
         }
     }
 
-    __device__ __forceinline__ void ld_ring(Row<T, V> &dst, int m) const {
-        const T *row = ring + (m & (kRing - 1)) * L::ROW_ELEMS + lane * V;
+    // y row (n - J) at phase PH = n % 3: a compile-time offset from one of the three group bases
+    template <int PH, int J>
+    __device__ __forceinline__ void ld_y(Row<T, V> &dst, const Groups &G) const {
+        constexpr int i = PH - J;
+        const T *row = (i >= 0) ? G.a + i * L::ROW_ELEMS : (i >= -3) ? G.b + (3 + i) * L::ROW_ELEMS : G.c + (6 + i) * L::ROW_ELEMS;
 #pragma unroll
         for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(row + f * L::SW, dst.f[f]);
     }
     __device__ __forceinline__ void ld_k(Row<T, V> &dst, const T *base, int slot) const {
-        const T *row = base + slot * L::ROW_ELEMS + lane * V;
+        const T *row = base + slot * L::ROW_ELEMS;
 #pragma unroll
         for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(row + f * L::SW, dst.f[f]);
     }
     __device__ __forceinline__ void st_k(const Row<T, V> &src, T *base, int slot) const {
-        T *row = base + slot * L::ROW_ELEMS + lane * V;
+        T *row = base + slot * L::ROW_ELEMS;
 #pragma unroll
         for (int f = 0; f < 3; ++f) SmemIO<T, V>::st(row + f * L::SW, src.f[f]);
     }
@@ -177,9 +198,6 @@ struct SweepT {
         }
     }
 
-    // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
-    static constexpr bool kPacked = std::is_same<T, float>::value && V == 2 && RECIP;
-
     __device__ __forceinline__ void tendency_row(const Row<T, V> &U, const Row<T, V> &C, const Row<T, V> &D,
                                                  Row<T, V> &k) const {
         T Lft[3], Rgt[3];
@@ -191,11 +209,9 @@ struct SweepT {
         if constexpr (kPacked) {
             auto P = [](const T(&r)[V]) { return F2{(float)r[0], (float)r[1]}; };
             F2 du, dv, dh;
-            tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]),
-                          F2{(float)Lft[0], (float)C.f[0][0]}, F2{(float)C.f[0][1], (float)Rgt[0]}, P(U.f[0]), P(D.f[0]),
-                          F2{(float)Lft[1], (float)C.f[1][0]}, F2{(float)C.f[1][1], (float)Rgt[1]}, P(U.f[1]), P(D.f[1]),
-                          F2{(float)Lft[2], (float)C.f[2][0]}, F2{(float)C.f[2][1], (float)Rgt[2]}, P(U.f[2]), P(D.f[2]),
-                          du, dv, dh);
+            tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]), (float)Lft[0], (float)Rgt[0], P(U.f[0]), P(D.f[0]),
+                          (float)Lft[1], (float)Rgt[1], P(U.f[1]), P(D.f[1]), (float)Lft[2], (float)Rgt[2], P(U.f[2]),
+                          P(D.f[2]), du, dv, dh);
             k.f[0][0] = du.x; k.f[0][1] = du.y;
             k.f[1][0] = dv.x; k.f[1][1] = dv.y;
             k.f[2][0] = dh.x; k.f[2][1] = dh.y;
@@ -233,7 +249,7 @@ struct SweepT {
 
     // Stage S1 (1-based) at iteration n; PH = n % 3. Center row index m = n - S1.
     template <int PH, int S1, bool FAST>
-    __device__ __forceinline__ void stage(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
+    __device__ __forceinline__ void stage(Windows &Lv, int n, const Groups &G) const {
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
         if (!FAST) {
@@ -252,13 +268,13 @@ struct SweepT {
         Row<T, V> k, yb;
         if constexpr (S1 == 1) {
             Row<T, V> U, D;
-            ld_ring(U, n - 2);
-            ld_ring(yb, n - 1);
-            ld_ring(D, n);
+            ld_y<PH, 2>(U, G);
+            ld_y<PH, 1>(yb, G);
+            ld_y<PH, 0>(D, G);
             tendency_row(U, yb, D, k);
         } else {
             tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k);
-            ld_ring(yb, n - S1);
+            ld_y<PH, S1>(yb, G);
         }
         if constexpr (S1 < NST) {
             const T c = (NST == 4 && S1 == 3) ? a.dt : a.half_dt;
@@ -267,9 +283,9 @@ struct SweepT {
                 const F2 c2 = f2_splat((float)c);
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    const F2 r = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, c2,
-                                           F2{(float)k.f[f][0], (float)k.f[f][1]});
-                    t.f[f][0] = r.x; t.f[f][1] = r.y;
+                    const F2 rr = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, c2,
+                                            F2{(float)k.f[f][0], (float)k.f[f][1]});
+                    t.f[f][0] = rr.x; t.f[f][1] = rr.y;
                 }
             } else {
 #pragma unroll
@@ -285,23 +301,23 @@ struct SweepT {
                 }
             }
             if constexpr (NST == 4 && S1 == 2) st_k(k, k2s, m3);
-            if constexpr (NST == 4 && S1 == 3) st_k(k, k3s, (n - S1) & 1);
+            if constexpr (NST == 4 && S1 == 3) st_k(k, k3s, m3);
         } else {
             Row<T, V> o;
             if constexpr (NST == 4) {
                 Row<T, V> k2, k3;
                 ld_k(k2, k2s, m3);
-                ld_k(k3, k3s, (n - S1) & 1);
+                ld_k(k3, k3s, m3);
                 // reference aliasing: "k1" reads k4 at the combine (weather_simulation.cpp:350-351, F5)
                 if constexpr (kPacked) {
                     const F2 dt6 = f2_splat((float)a.dt6);
 #pragma unroll
                     for (int f = 0; f < 3; ++f) {
                         const F2 k4 = F2{(float)k.f[f][0], (float)k.f[f][1]};
-                        const F2 r = rk4_combine_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt6, k4,
-                                                      F2{(float)k2.f[f][0], (float)k2.f[f][1]},
-                                                      F2{(float)k3.f[f][0], (float)k3.f[f][1]}, k4);
-                        o.f[f][0] = r.x; o.f[f][1] = r.y;
+                        const F2 rr = rk4_combine_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt6, k4,
+                                                       F2{(float)k2.f[f][0], (float)k2.f[f][1]},
+                                                       F2{(float)k3.f[f][0], (float)k3.f[f][1]}, k4);
+                        o.f[f][0] = rr.x; o.f[f][1] = rr.y;
                     }
                 } else {
 #pragma unroll
@@ -314,9 +330,9 @@ struct SweepT {
                 const F2 dt2 = f2_splat((float)a.dt);
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    const F2 r = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt2,
-                                           F2{(float)k.f[f][0], (float)k.f[f][1]});
-                    o.f[f][0] = r.x; o.f[f][1] = r.y;
+                    const F2 rr = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt2,
+                                            F2{(float)k.f[f][0], (float)k.f[f][1]});
+                    o.f[f][0] = rr.x; o.f[f][1] = rr.y;
                 }
             } else {
 #pragma unroll
@@ -329,41 +345,52 @@ struct SweepT {
     }
 
     template <int PH, bool FAST>
-    __device__ __forceinline__ void stages(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
-        stage<PH, 1, FAST>(Lv, n);
-        if constexpr (NST >= 2) stage<PH, 2, FAST>(Lv, n);
+    __device__ __forceinline__ void iteration(Windows &Lv, int n, const Groups &G) const {
+        stage<PH, 1, FAST>(Lv, n, G);
+        if constexpr (NST >= 2) stage<PH, 2, FAST>(Lv, n, G);
         if constexpr (NST >= 4) {
-            stage<PH, 3, FAST>(Lv, n);
-            stage<PH, 4, FAST>(Lv, n);
+            stage<PH, 3, FAST>(Lv, n, G);
+            stage<PH, 4, FAST>(Lv, n, G);
         }
     }
 
-    template <int PH>
-    __device__ __forceinline__ void iteration(Row<T, V> (&Lv)[(NST > 1 ? NST - 1 : 1)][3], int n) const {
-        wait_row(n);
-        const int r_last = y0 - NST + n - NST;  // center row of the final stage (smallest row touched)
-        const int r_first = y0 - NST + n - 1;   // center row of stage 1 (largest)
-        const bool fast = !edge_strip && n >= 2 * NST && r_last > gmin && r_first < gmax;
-        if (fast) stages<PH, true>(Lv, n);
-        else stages<PH, false>(Lv, n);
-        __syncwarp();
-        // the oldest row is dead now: re-arm its slot with the row kRing ahead
-        constexpr int KEEP = NST > 2 ? NST : 2;
-        const int dead = n - KEEP;
-        // (generic-proxy reads of the slot are complete: their values were consumed before the __syncwarp)
-        if (lane == 0 && dead >= 0 && dead + kRing < niter) issue_row(dead + kRing);
+    // After iteration 3q of triple q the rows of triple q-2 are dead: their group takes the rows of triple q+1.
+    __device__ __forceinline__ void refill(int q) const {
+        __syncwarp();  // every lane has consumed its reads of the dead group
+        if (lane == 0) issue_group(q + 1);
     }
 
     __device__ __forceinline__ void run() const {
-        Row<T, V> Lv[(NST > 1 ? NST - 1 : 1)][3];
-        int n = 0;
-        for (; n + 3 <= niter; n += 3) {
-            iteration<0>(Lv, n);
-            iteration<1>(Lv, n + 1);
-            iteration<2>(Lv, n + 2);
+        Windows Lv;
+        Groups G;
+        const T *base = ring + lane * V;
+        G.a = base;                            // group 0: rows of triple 0
+        G.b = base + 2 * 3 * L::ROW_ELEMS;     // group 2 (triple -1: never read)
+        G.c = base + 1 * 3 * L::ROW_ELEMS;     // group 1 (triple -2: never read; next to be filled)
+        const int ntriples = (niter + 2) / 3;
+        for (int q = 0; q < ntriples; ++q) {
+            const int n = 3 * q;
+            wait_group(q);
+            // steady state: pipeline full, no domain edge within reach of any stage, interior strip
+            const int r_last = y0 - NST + n - NST;      // smallest center row touched in this triple
+            const int r_first = y0 - NST + (n + 2) - 1; // largest
+            const bool fast = !edge_strip && n >= 2 * NST && n + 2 < niter && r_last > gmin && r_first < gmax;
+            if (fast) {
+                iteration<0, true>(Lv, n, G);
+                refill(q);
+                iteration<1, true>(Lv, n + 1, G);
+                iteration<2, true>(Lv, n + 2, G);
+            } else {
+                iteration<0, false>(Lv, n, G);
+                refill(q);
+                if (n + 1 < niter) iteration<1, false>(Lv, n + 1, G);
+                if (n + 2 < niter) iteration<2, false>(Lv, n + 2, G);
+            }
+            const T *t = G.c;  // rotate: triple q+1 lives where triple q-2 lived
+            G.c = G.b;
+            G.b = G.a;
+            G.a = t;
         }
-        if (n < niter) iteration<0>(Lv, n);
-        if (n + 1 < niter) iteration<1>(Lv, n + 1);
     }
 };
 
@@ -397,7 +424,7 @@ __global__ void __launch_bounds__(32, MINB)
     sw.out_hi = min(sw.out_lo + L::OUTW, g.W);
     sw.lvl_off = (long long)blockIdx.z * g.level_stride;
     sw.ring = reinterpret_cast<T *>(smem_raw);
-    sw.k2s = sw.ring + kRing * L::ROW_ELEMS;
+    sw.k2s = sw.ring + kRing * L::ROW_ELEMS + lane * V;
     sw.k3s = sw.k2s + 3 * L::ROW_ELEMS;
     sw.ring_u32 = smem_u32(sw.ring);
     sw.bar_u32 = smem_u32(smem_raw + (kRing + L::K_ROWS) * L::ROW_BYTES);
@@ -412,11 +439,10 @@ __global__ void __launch_bounds__(32, MINB)
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kRing; ++s) mbar_init(sw.bar_u32 + 8u * s, 1);
+        for (int s = 0; s < kGroups; ++s) mbar_init(sw.bar_u32 + 8u * s, 1);
         fence_mbar_init();
         fence_proxy_async();
-        const int pre = min(kRing, sw.niter);
-        for (int m = 0; m < pre; ++m) sw.issue_row(m);
+        sw.issue_group(0);
     }
     __syncwarp();
     sw.run();
@@ -459,7 +485,7 @@ cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float
     switch (nstages) {
         case 1: return launch_impl<float, 1, 2, 20>(g, ph, a, st);
         case 2: return launch_impl<float, 2, 2, 16>(g, ph, a, st);
-        case 4: return launch_impl<float, 4, 2, 16>(g, ph, a, st);
+        case 4: return launch_impl<float, 4, 2, 20>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
 }

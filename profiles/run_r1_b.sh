@@ -6,7 +6,7 @@ B="python bench.py --no-cpu-baseline --no-e2e"
 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log
 tail -12 gpurun_out/pytest.log
 {
-for k in step_fused_tma; do for rpc in 64 96 128 192; do
+for k in step_fused_tma; do for rpc in 64 128 256; do
   echo "== $k RPC=$rpc"; WSB_FUSED_ROWS_PER_CHUNK=$rpc $B --kernel $k --steps 30 --warmup 5 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['clocks'])"
 done; done
 echo "== step_fused_reg MINB=12 RPC=64"; WSB_FUSED_MINB=12 WSB_FUSED_ROWS_PER_CHUNK=64 $B --kernel step_fused_reg --steps 30 --warmup 5 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['clocks'])"
