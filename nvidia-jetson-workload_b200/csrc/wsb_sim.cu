@@ -200,8 +200,8 @@ struct wsb_sim {
     void *k3[3] = {nullptr, nullptr, nullptr};
     bool diag_dirty = false;  // vorticity/divergence need recomputing from the current u, v
     bool halo_valid = false;  // ghost rows of the current state are up to date (nranks > 1)
-    cudaStream_t stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr;
+    cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr, ev_interior = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
     bool run_open = false;    // ev_start recorded, ev_stop pending
     double last_run_ms = 0.0;
@@ -340,11 +340,18 @@ static int enqueue_step_stages(wsb_sim *s) {
 }
 
 template <typename T>
-static cudaError_t launch_step(const wsb_sim *s, const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a) {
-    return s->path == PATH_STEP_TMA ? launch_step_tma<T>(g, ph, a, s->nstages, s->stream)
-                                    : launch_step_fused<T>(g, ph, a, s->nstages, s->stream);
+static cudaError_t launch_step(const wsb_sim *s, const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a,
+                               cudaStream_t st) {
+    return s->path == PATH_STEP_TMA ? launch_step_tma<T>(g, ph, a, s->nstages, st)
+                                    : launch_step_fused<T>(g, ph, a, s->nstages, st);
 }
 
+// Whole-step kernels. Single GPU: one launch per step. Row slabs: the `halo` rows next to each slab edge
+// need the neighbours' ghost rows, the rest does not, so a step is
+//   edge stream (high priority): wait ghosts + previous interior -> ONE launch over both edge bands -> ev_edge
+//   comm stream                : wait ev_edge -> ncclSend/ncclRecv of the new edge rows -> ev_halo
+//   main stream                : wait previous ev_edge -> interior launch -> ev_interior
+// i.e. the edge bands and their exchange run beside the interior sweep instead of in front of it.
 template <typename T>
 static int enqueue_step_fused(wsb_sim *s) {
     const Geometry<T> g = s->cur.geom<T>();
@@ -361,27 +368,33 @@ static int enqueue_step_fused(wsb_sim *s) {
     const int halo = s->nstages;  // one ghost row per fused stage
     if (!s->comm) {
         a.y_begin = 0; a.y_end = H;
-        WSB_CUDA(launch_step<T>(s, g, ph, a));
+        WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
         s->metrics.kernel_launches += 1;
         return WSB_OK;
     }
-    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    // dependencies captured BEFORE this step re-records the events
+    WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_interior, 0));  // previous step's interior rows
+    WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_halo, 0));      // ghost rows of the current state
+    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));           // previous step's edge rows
+    // edge bands: rows [0, e) and [max(e, H-halo), H) in one launch, short chunks for parallelism
     const int e = std::min(halo, H);
-    a.y_begin = 0; a.y_end = e;
-    WSB_CUDA(launch_step<T>(s, g, ph, a));
+    StepArgs<T> b = a;
+    b.y_begin = 0; b.y_end = e;
+    b.y_begin2 = std::max(e, H - halo); b.y_end2 = H;
+    b.rows_per_chunk = 2;
+    WSB_CUDA(launch_step<T>(s, g, ph, b, s->edge_stream));
     s->metrics.kernel_launches += 1;
-    if (H > e) {
-        a.y_begin = std::max(e, H - halo); a.y_end = H;
-        WSB_CUDA(launch_step<T>(s, g, ph, a));
-        s->metrics.kernel_launches += 1;
-    }
-    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->edge_stream));
     WSB_TRY(sim_exchange(s, s->next, halo, s->ev_edge));
     if (H > 2 * halo) {
         a.y_begin = halo; a.y_end = H - halo;
-        WSB_CUDA(launch_step<T>(s, g, ph, a));
+        WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
         s->metrics.kernel_launches += 1;
     }
+    WSB_CUDA(cudaEventRecord(s->ev_interior, s->stream));
+    // keep the main stream a superset of the edge stream: whatever is enqueued on it next (the next interior
+    // sweep, a read-back, diagnostics) sees this step's edge rows
+    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
     return WSB_OK;
 }
 
@@ -408,7 +421,8 @@ static int enqueue_primitive_tp(wsb_sim *s) {
 static int sim_ensure_halo(wsb_sim *s) {
     if (!s->comm || s->halo_valid) return WSB_OK;
     void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
-    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));      // "the current state is complete" for the comm stream
+    WSB_CUDA(cudaEventRecord(s->ev_interior, s->stream));  // ... and for the edge stream
     const int depth = is_step_path(s->path) ? s->nstages : 1;
     WSB_TRY(sim_exchange(s, cur3, depth, s->ev_edge));
     s->halo_valid = true;
@@ -451,7 +465,12 @@ static int sim_begin_timing(wsb_sim *s) {
 
 static int sim_sync(wsb_sim *s) {
     WSB_CUDA(cudaSetDevice(s->cur.device));
+    if (s->comm) {  // the timed region ends when the edge bands and the ghost-row exchange have finished too
+        WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
+        WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    }
     if (s->run_open) WSB_CUDA(cudaEventRecord(s->ev_stop, s->stream));
+    if (s->edge_stream) WSB_CUDA(cudaStreamSynchronize(s->edge_stream));
     if (s->comm_stream) WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
     WSB_CUDA(cudaStreamSynchronize(s->stream));
     if (s->run_open) {
@@ -751,16 +770,18 @@ static void sim_free(wsb_sim *s) {
     cudaSetDevice(s->cur.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->edge_stream) cudaStreamSynchronize(s->edge_stream);
     if (s->comm) halo_comm_destroy(s->comm);
     sim_free3(s->next); sim_free3(s->tA); sim_free3(s->tB); sim_free3(s->k1); sim_free3(s->k2); sim_free3(s->k3);
     for (int k = 0; k < WSB_NUM_FIELDS; ++k)
         if (s->alt[k].base) cudaFree(s->alt[k].base);
     if (s->d_partial) cudaFree(s->d_partial);
     grid_fini(&s->cur);
-    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1};
+    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -819,7 +840,7 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         if (st != WSB_OK) break;
         s->cur.owner = s;
         for (int k = 0; k < WSB_NUM_FIELDS; ++k) s->alt[k].uniform = (double)kResetValue[k];
-        cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1};
+        cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1, &s->ev_interior};
         for (cudaEvent_t *e : evs)
             if (cudaEventCreate(e) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
         if (st != WSB_OK) break;
@@ -866,7 +887,10 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         if (st != WSB_OK) break;
 
         if (c.nranks > 1) {
-            if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            if (cudaStreamCreateWithPriority(&s->edge_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
                 st = cuda_fail(cudaGetLastError(), "cudaStreamCreate(comm)", __FILE__, __LINE__);
                 break;
             }

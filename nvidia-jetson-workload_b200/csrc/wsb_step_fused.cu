@@ -295,8 +295,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x;
     if (strip * OUTW >= g.W) return;  // warp-uniform
-    const int y0 = a.y_begin + blockIdx.y * rows_per_chunk;
-    const int y1 = min(y0 + rows_per_chunk, a.y_end);
+    // blockIdx.y enumerates the chunks of the first row range, then those of the optional second one
+    const int nchunks1 = (a.y_end - a.y_begin + rows_per_chunk - 1) / rows_per_chunk;
+    const bool second = (int)blockIdx.y >= nchunks1;
+    const int cy = second ? (int)blockIdx.y - nchunks1 : (int)blockIdx.y;
+    const int y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
+    const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
     if (y0 >= y1) return;
 
     Sweep<T, NST, V, RECIP> sw(g, ph, a);
@@ -333,12 +337,13 @@ int minb_variant() {
 
 template <typename T, int NST, int V, int MINB>
 cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
-    const int rows = a.y_end - a.y_begin;
+    const int rows = a.y_end - a.y_begin, rows2 = a.y_end2 - a.y_begin2;
     if (rows <= 0) return cudaSuccess;
     constexpr int OUTW = 32 * V - 2 * ((NST + V - 1) / V * V);
     const int strips = (g.W + OUTW - 1) / OUTW;
-    const int rpc = rows_per_chunk_default();
-    const dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, (rows + rpc - 1) / rpc, g.L);
+    const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk : rows_per_chunk_default();
+    const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
+    const dim3 grid((strips + kWarpsPerCta - 1) / kWarpsPerCta, chunks, g.L);
     const dim3 block(kWarpsPerCta * 32);
     if (ph.recip) step_fused_kernel<T, NST, V, true, MINB><<<grid, block, 0, st>>>(g, ph, a, rpc);
     else step_fused_kernel<T, NST, V, false, MINB><<<grid, block, 0, st>>>(g, ph, a, rpc);

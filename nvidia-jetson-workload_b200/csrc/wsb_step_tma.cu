@@ -401,8 +401,12 @@ __global__ void __launch_bounds__(32, MINB)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int strip = blockIdx.x;
-    const int y0 = a.y_begin + blockIdx.y * rows_per_chunk;
-    const int y1 = min(y0 + rows_per_chunk, a.y_end);
+    // blockIdx.y enumerates the chunks of the first row range, then those of the optional second one
+    const int nchunks1 = (a.y_end - a.y_begin + rows_per_chunk - 1) / rows_per_chunk;
+    const bool second = (int)blockIdx.y >= nchunks1;
+    const int cy = second ? (int)blockIdx.y - nchunks1 : (int)blockIdx.y;
+    const int y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
+    const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
     if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform
 
     SweepT<T, NST, V, RECIP> sw(g, ph, a);
@@ -454,18 +458,21 @@ int env_int(const char *name, int dflt) {
 }
 
 int rows_per_chunk_default() {
-    static const int v = env_int("WSB_FUSED_ROWS_PER_CHUNK", 128);
-    return v > 0 ? v : 128;
+    // 64 rows + 8 pipeline-fill rows per warp: 12.5 % redundant sweep, ~19 k warps on 8192^2 (measured best
+    // among 32/64/96/128/192/256 on B200, profiles/r1/sweep_step_fused_tma.log)
+    static const int v = env_int("WSB_FUSED_ROWS_PER_CHUNK", 64);
+    return v > 0 ? v : 64;
 }
 
 template <typename T, int NST, int V, int MINB>
 cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
     using L = Layout<T, NST, V>;
-    const int rows = a.y_end - a.y_begin;
+    const int rows = a.y_end - a.y_begin, rows2 = a.y_end2 - a.y_begin2;
     if (rows <= 0) return cudaSuccess;
     const int strips = (g.W + L::OUTW - 1) / L::OUTW;
-    const int rpc = rows_per_chunk_default();
-    const dim3 grid(strips, (rows + rpc - 1) / rpc, g.L);
+    const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk : rows_per_chunk_default();
+    const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
+    const dim3 grid(strips, chunks, g.L);
     if (ph.recip) step_tma_kernel<T, NST, V, true, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
     else step_tma_kernel<T, NST, V, false, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
     return cudaGetLastError();
