@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the weather-sim time-stepping hot path on B200 (contract: see the task statement).
+"""Benchmark of the weather-sim time-stepping hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--kernel auto|stage_direct|step_fused_reg|step_fused_tma]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload NAME] [--kernel auto|stage_direct|step_fused_reg|step_fused_tma]
 
-Metric (BASELINE.json): grid cell-updates/s of the RK4 Shallow-Water step. A "step" is one full RK4 time
-step over the whole grid. N = 1 runs BASELINE config 2 (SWE 8192x8192 fp32 RK4); N > 1 is weak scaling with
-the same 8192x8192 slab per GPU (global grid 8192 x 8192*N, row slabs, NCCL ghost-row exchange inside
-libweather_b200.so). One process per GPU; torch.distributed (NCCL) is used only for the barrier and the
-max-over-ranks reduction of the timings.
+Metric (BASELINE.json): grid cell-updates/s of the RK4 Shallow-Water step. A "step" is one full time step
+over the whole grid. The default workload is BASELINE config 2 (SWE 8192x8192 fp32 RK4) at N = 1 and weak
+scaling of it at N > 1 (the same 8192x8192 row slab per GPU, global grid 8192 x 8192*N, NCCL ghost-row
+exchange inside libweather_b200.so). One process per GPU (torchrun); torch.distributed (NCCL) is used only
+for the barrier and the max-over-ranks reduction of the timings -- the product path never imports torch.
+
+Other BASELINE configs are available as --workload (their lines carry their own metric name):
+    swe8192_euler   SWE 8192^2 fp32 Euler            (1 fused pass, 24 B/cell-step: the HBM-bound case)
+    baro16384_f64   Barotropic 16384^2 fp64 "RK4"    (reference semantics: SWE tendencies + RK2)
+    prim2048x64     Primitive 2048^2 x 64 levels fp32 RK2 (+ constant T/p drift)
+    swe32768_rk4    SWE 32768^2 fp32 RK4, STRONG scaling: the global grid is split over the N GPUs
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/libws_ref.so, the patched
-reference build; the oracle port if that is absent) on the host cores, on a bounded band of the same
-workload.
+reference build; the oracle port if that is absent) on the host cores, on a bounded band of the workload.
 """
 import argparse
 import json
@@ -25,13 +31,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(ROOT, "nvidia-jetson-workload_b200")]
 
-METRIC = "grid cell-updates/sec (RK4 SWE step)"
 UNIT = "cell-updates/s"
-GRID_W = 8192
-ROWS_PER_GPU = 8192
-# Algorithmic bytes per cell per step (S = 4 bytes):
-BYTES_PER_CELL_STEP_4PASS = 168   # one fused pass per RK stage (4 launches per step)
-BYTES_PER_CELL_STEP_FUSED = 24    # whole step in one pass: read y_n (3 fields), write y_{n+1} (3 fields)
+# bpc_stage / bpc_step: algorithmic bytes per cell per step of a one-pass-per-RK-stage
+# design and of the whole-step kernels (read y_n once, write y_n+1 once; + T,p read/write for Primitive).
+WORKLOADS = {
+    "swe8192_rk4": dict(W=8192, rows=8192, model="shallow_water", integ="rk4", dtype="f32", levels=1,
+                        scaling="weak", metric="grid cell-updates/sec (RK4 SWE step)",
+                        desc="SWE {W}x{H} fp32 RK4 (reference-parity combine)", bpc_stage=168, bpc_step=24),
+    "swe8192_euler": dict(W=8192, rows=8192, model="shallow_water", integ="euler", dtype="f32", levels=1,
+                          scaling="weak", metric="grid cell-updates/sec (Euler SWE step)",
+                          desc="SWE {W}x{H} fp32 Euler", bpc_stage=24, bpc_step=24),
+    "baro16384_f64": dict(W=16384, rows=16384, model="barotropic", integ="rk4", dtype="f64", levels=1,
+                          scaling="weak", metric="grid cell-updates/sec (Barotropic fp64 RK4->RK2 step)",
+                          desc="Barotropic {W}x{H} fp64, RK4 requested = SWE tendencies + RK2 (reference semantics)",
+                          bpc_stage=120, bpc_step=48),
+    "prim2048x64": dict(W=2048, rows=2048, model="primitive", integ="rk2", dtype="f32", levels=64,
+                        scaling="weak", metric="grid cell-updates/sec (Primitive 64-level RK2 step)",
+                        desc="Primitive {W}x{H}x64 levels fp32 RK2 (SWE tendencies per level + constant T/p drift)",
+                        bpc_stage=100, bpc_step=40),
+    "swe32768_rk4": dict(W=32768, rows=32768, model="shallow_water", integ="rk4", dtype="f32", levels=1,
+                         scaling="strong", metric="grid cell-updates/sec (RK4 SWE step)",
+                         desc="SWE {W}x{H} fp32 RK4 (reference-parity combine), strong scaling",
+                         bpc_stage=168, bpc_step=24),
+}
 
 
 def measured_peaks():
@@ -46,7 +68,7 @@ def measured_peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period_s=0.01):
+    def __init__(self, index, period_s=0.005):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -107,23 +129,40 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+INTEG_CODE = {"euler": 0, "rk2": 1, "rk4": 2}
+MODEL_CODE = {"shallow_water": 0, "barotropic": 1, "primitive": 2}
+
+
+def fill_bump_slab(h, r0, W, H_global):
+    """Gaussian height bump centred on the GLOBAL grid (IC-A), written row-block wise."""
+    sigma = 0.1 * min(W, H_global)
+    xx = (np.arange(W, dtype=np.float64)[None, :] - (W - 1) / 2.0) ** 2
+    nrows = h.shape[-2]
+    for b in range(0, nrows, 512):
+        e = min(b + 512, nrows)
+        yy = (np.arange(r0 + b, r0 + e, dtype=np.float64)[:, None] - (H_global - 1) / 2.0) ** 2
+        h[..., b:e, :] = (10.0 + np.exp(-(xx + yy) / (2.0 * sigma * sigma))).astype(h.dtype)
+
+
 # ------------------------------------------------------------------------------ reference arm --
-def time_reference_cpu(width, rows, steps, warmup, integ=2):
+def time_reference_cpu(width, rows, steps, warmup, model=0, integ=2):
     """Times the reference's CPU implementation (weather_simulation.cpp:117-158) on a (rows x width) band."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
-    from weather_sim import synthetic as syn
 
     cores = host_threads()
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    u, v, h = syn.gaussian_bump(width, rows)
+    h = np.empty((rows, width), np.float32)
+    fill_bump_slab(h, 0, width, rows)
+    u = np.zeros_like(h)
+    v = np.zeros_like(h)
     if oracle_py.reference_available():
         kind = "reference"
-        sim = oracle_py.Reference(width, rows, 0, integ, coriolis_f=0.1)
+        sim = oracle_py.Reference(width, rows, model, integ, coriolis_f=0.1)
     else:
         kind = "port"
         oracle_py.build_oracle()
-        sim = oracle_py.Oracle(width, rows, 0, integ, coriolis_f=0.1)
+        sim = oracle_py.Oracle(width, rows, model, integ, coriolis_f=0.1)
     sim.set_state(u, v, h)
     if warmup:
         sim.step(warmup)
@@ -135,24 +174,25 @@ def time_reference_cpu(width, rows, steps, warmup, integ=2):
             "ms_per_step": dt / steps * 1e3}
 
 
-def reference_band_rows(total_steps, budget_s=100.0, rate=8.0e6):
-    cells = budget_s * rate / max(total_steps, 1)
-    return int(min(ROWS_PER_GPU, max(64, cells // GRID_W)))
-
-
-def run_reference_arm(args, rank):
+def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
-    rows = reference_band_rows(args.steps + args.warmup)
-    r = time_reference_cpu(GRID_W, rows, args.steps, args.warmup)
-    sample = (f"{r['kind']} CPU path (oracle/_ref, OpenMP, {r['cores']} threads) on an {GRID_W}x{rows} band of the "
-              f"{GRID_W}x{ROWS_PER_GPU} workload, {args.steps} RK4 steps after {args.warmup} warm-up")
+    W = wl["W"]
+    # a band of the workload sized so that K + W steps finish in ~100 s at the reference's ~8 Mcell/s (RK4)
+    rate = 8.0e6 if wl["integ"] != "euler" else 40.0e6
+    cells = 100.0 * rate / max(args.steps + args.warmup, 1)
+    rows = int(min(wl["rows"], max(64, cells // W)))
+    r = time_reference_cpu(W, rows, args.steps, args.warmup, MODEL_CODE[wl["model"]], INTEG_CODE[wl["integ"]])
+    note = "" if wl["dtype"] == "f32" and wl["levels"] == 1 else \
+        " (the reference computes in fp32 on a single 2-D level whatever the configuration asks, SURVEY.md F7-F8)"
+    sample = (f"{r['kind']} CPU path (oracle/_ref, OpenMP, {r['cores']} threads) on a {W}x{rows} band of the "
+              f"workload, {args.steps} steps after {args.warmup} warm-up{note}")
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SWE {GRID_W}x{ROWS_PER_GPU} fp32 RK4 (reference CPU implementation on a bounded band)",
-                   "band_rows": rows, "ic": "gaussian_bump"},
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"].format(W=W, H=wl["rows"]) + " -- reference CPU implementation on a bounded band",
+                   "name": args.workload, "band_rows": rows, "ic": "gaussian_bump"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -161,10 +201,9 @@ def run_reference_arm(args, rank):
 
 
 # ----------------------------------------------------------------------------------- our arm --
-def run_b200_arm(args, rank, world, local_rank):
+def run_b200_arm(args, wl, rank, world, local_rank):
     from weather_sim import _capi
     from weather_sim import distributed as wd
-    from weather_sim import synthetic as syn
 
     dist = None
     if world > 1:
@@ -186,20 +225,23 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    H_global = ROWS_PER_GPU * world
+    W, L = wl["W"], wl["levels"]
+    H_global = wl["rows"] * world if wl["scaling"] == "weak" else wl["rows"]
+    np_dtype = np.float64 if wl["dtype"] == "f64" else np.float32
+    esize = np.dtype(np_dtype).itemsize
     nccl_id = wd.share_nccl_id() if world > 1 else None
-    sim = _capi.Simulation(GRID_W, H_global, model="shallow_water", integrator="rk4", coriolis_f=0.1, max_time=1e30,
-                           kernel=args.kernel, device_id=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    sim = _capi.Simulation(W, H_global, model=wl["model"], integrator=wl["integ"], coriolis_f=0.1, max_time=1e30,
+                           dtype=np_dtype, num_levels=L, kernel=args.kernel, device_id=local_rank, rank=rank,
+                           nranks=world, nccl_id=nccl_id)
     r0, nrows = sim.local_rows
-    # synthetic initial condition: Gaussian height bump centred on the GLOBAL grid; each rank fills its slab
-    yy = np.arange(r0, r0 + nrows, dtype=np.float64)[:, None]
-    xx = np.arange(GRID_W, dtype=np.float64)[None, :]
-    sigma = 0.1 * min(GRID_W, H_global)
-    hb = _capi.pinned_empty((nrows, GRID_W), np.float32)
-    ub = _capi.pinned_empty((nrows, GRID_W), np.float32)
-    vb = _capi.pinned_empty((nrows, GRID_W), np.float32)
-    hb[...] = (10.0 + np.exp(-((xx - (GRID_W - 1) / 2.0) ** 2 + (yy - (H_global - 1) / 2.0) ** 2)
-                             / (2.0 * sigma * sigma))).astype(np.float32)
+    shape = (nrows, W) if L == 1 else (L, nrows, W)
+    hb = _capi.pinned_empty(shape, np_dtype)
+    ub = _capi.pinned_empty(shape, np_dtype)
+    vb = _capi.pinned_empty(shape, np_dtype)
+    fill_bump_slab(hb, r0, W, H_global)
+    if L > 1:  # per-level amplitude (1 + k/64), SURVEY.md section 8d C4
+        for k in range(1, L):
+            hb[k] = 10.0 + (1.0 + k / 64.0) * (hb[0] - 10.0)
     ub[...] = 0.0
     vb[...] = 0.0
     sim.set_state(ub, vb, hb)
@@ -215,81 +257,86 @@ def run_b200_arm(args, rank, world, local_rank):
     barrier()
     launches = sim.metrics.kernel_launches - launches0
     ms = max_over_ranks(dev_ms)
-    cells_total = GRID_W * H_global
+    cells_total = W * H_global * L
+    cells_rank = W * nrows * L
     value = cells_total * args.steps / (ms * 1e-3)
-    halo_ms = sim.metrics.halo_time_ms
 
     # ---- end to end through the C-ABI with HOST buffers: H2D state, one step, D2H state, every step ----
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 10))
-    outs = [_capi.pinned_empty((nrows, GRID_W), np.float32) for _ in range(3)]
-    for _ in range(2 if e2e_steps else 0):  # warm-up of the copy path
-        sim.set_state(ub, vb, hb)
-        sim.step(1)
-        for n, o in zip(("u", "v", "h"), outs):
-            sim.get_field(n, out=o)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sim.set_state(ub, vb, hb)
-        sim.step(1)
-        for n, o in zip(("u", "v", "h"), outs):
-            sim.get_field(n, out=o)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = cells_total * e2e_steps / e2e_s if e2e_steps else None
-    field_bytes = nrows * GRID_W * 4
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 10))
+        outs = [_capi.pinned_empty(shape, np_dtype) for _ in range(3)]
+
+        def e2e_step():
+            sim.set_state(ub, vb, hb)
+            sim.step(1)
+            for n, o in zip(("u", "v", "h"), outs):
+                sim.get_field(n, out=o)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": cells_total * e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": 3 * cells_total * esize, "d2h_bytes_per_step": 3 * cells_total * esize,
+               "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+               "api": "weather_sim._capi (ctypes over the C-ABI): set u,v,h from pinned host arrays, step(), get "
+                      "u,v,h into pinned host arrays -- every step"}
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
         kernel = sim.kernel_name
-        launches_per_step = launches / max(args.steps, 1)
-        bpc = BYTES_PER_CELL_STEP_FUSED if kernel.startswith("step_fused") else BYTES_PER_CELL_STEP_4PASS
-        cells_rank = GRID_W * nrows
+        fused = kernel.startswith("step_fused")
+        bpc = wl["bpc_step"] if fused else wl["bpc_stage"]
         achieved = bpc * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_kind": peak_kind, "kernel": kernel,
             "algorithmic_bytes_per_cell_step": bpc,
-            "launches_per_step": launches_per_step,
-            "equivalent_4pass_gbs": BYTES_PER_CELL_STEP_4PASS * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9,
-            "note": ("step_fused keeps all four RK stages in registers: it moves 24 B/cell-step instead of the "
-                     "168 B/cell-step of the one-pass-per-stage design and is bound by fp32 issue (no FMA allowed "
-                     "for bit parity), see DESIGN.md") if kernel.startswith("step_fused") else
-                    "one fused tendency+update pass per RK stage (4 launches per step), 168 B/cell-step",
+            "launches_per_step": launches / max(args.steps, 1),
+            "stage_per_pass_equivalent_gbs": wl["bpc_stage"] * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9,
+            "note": ("whole-step kernel: every RK stage stays on chip, HBM sees one read of y_n and one write of "
+                     "y_n+1 per step (%d B/cell-step instead of %d with one pass per stage); for RK4 fp32 the "
+                     "kernel is bound by fp32 issue, not HBM (no FMA allowed for bit parity) -- DESIGN.md section 4"
+                     % (wl["bpc_step"], wl["bpc_stage"])) if fused else
+                    "one fused tendency+update pass per RK stage",
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
                 with open(traffic_file) as f:
-                    roofline["traffic"] = json.load(f).get(kernel)
+                    roofline["traffic"] = json.load(f).get(args.workload, {}).get(kernel)
             except Exception:
                 pass
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            rows = 2048
-            r = time_reference_cpu(2048, rows, 20, 2)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                   "sample": f"SWE 2048x2048 fp32 RK4, 20 steps after 2 warm-up ({r['seconds']:.1f} s); the "
-                             f"reference's RK4 throughput is flat in grid size (BASELINE.md section 2)"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"SWE {GRID_W}x{H_global} fp32 RK4 (reference-parity combine), dt=0.01, f=0.1, "
-                                   f"Gaussian bump; {GRID_W}x{ROWS_PER_GPU} row slab per GPU",
-                       "grid": [H_global, GRID_W], "kernel": kernel, "decomposition": f"row-slabs x{world}",
-                       "cache": "inputs larger than L2 (805 MB state per GPU per step vs 126 MB L2)"},
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": wl["scaling"], "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["desc"].format(W=W, H=H_global) + ", dt=0.01, g=9.81, f=0.1, Gaussian bump",
+                       "name": args.workload, "grid": [H_global, W] if L == 1 else [L, H_global, W],
+                       "kernel": kernel, "decomposition": f"row-slabs x{world} ({nrows} rows per GPU)",
+                       "cache": f"state per GPU ({3 * cells_rank * esize / 1e6:.0f} MB read per step) >> 126 MB L2: "
+                                "inputs larger than L2"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * field_bytes * world,
-                    "d2h_bytes_per_step": 3 * field_bytes * world, "steps": e2e_steps,
-                    "api": "weather_sim._capi (ctypes over the C-ABI): set u,v,h from pinned host arrays, step(), "
-                           "get u,v,h into pinned host arrays, every step"},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "halo_ms_last_exchange": halo_ms if world > 1 else None,
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world > 1:
+            line["halo_ms_last_exchange"] = sim.metrics.halo_time_ms
+        if world == 1 and not args.no_cpu_baseline:
+            n = 2048 if wl["integ"] != "euler" else 4096
+            steps = 20
+            r = time_reference_cpu(n, n, steps, 2, MODEL_CODE[wl["model"]], INTEG_CODE[wl["integ"]])
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                "sample": f"reference CPU path, {wl['model']} {n}x{n} fp32 {wl['integ']}, {steps} steps after 2 "
+                          f"warm-up ({r['seconds']:.1f} s); its throughput is flat in grid size (BASELINE.md section 2)"}
         print(json.dumps(line), flush=True)
     sim.close()
     if dist is not None:
@@ -303,20 +350,22 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="swe8192_rk4", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default="auto", choices=["auto", "stage_direct", "step_fused_reg", "step_fused_tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, wl, rank)
         return
-    if world != args.gpus and world == 1 and args.gpus > 1:
+    if world == 1 and args.gpus > 1:
         print(f"bench.py: --gpus {args.gpus} needs torchrun (WORLD_SIZE=1 here)", file=sys.stderr)
         sys.exit(2)
-    run_b200_arm(args, rank, world, local_rank)
+    run_b200_arm(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

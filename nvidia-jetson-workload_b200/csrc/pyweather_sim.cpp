@@ -739,8 +739,8 @@ PYBIND11_MODULE(pyweather_sim, m) {
 
     py::class_<WeatherSimulation>(m, "WeatherSimulation")
         .def(py::init<const SimulationConfig &>())
-        .def("set_initial_condition", &WeatherSimulation::set_initial_condition)
-        .def("set_output_manager", &WeatherSimulation::set_output_manager)
+        .def("set_initial_condition", &WeatherSimulation::set_initial_condition, py::keep_alive<1, 2>())
+        .def("set_output_manager", &WeatherSimulation::set_output_manager, py::keep_alive<1, 2>())
         .def("initialize", &WeatherSimulation::initialize)
         .def("run", &WeatherSimulation::run)
         .def("run_until", &WeatherSimulation::run_until)
