@@ -248,8 +248,8 @@ struct SweepT {
     }
 
     // Stage S1 (1-based) at iteration n; PH = n % 3. Center row index m = n - S1.
-    template <int PH, int S1, bool FAST>
-    __device__ __forceinline__ void stage(Windows &Lv, int n, const Groups &G) const {
+    template <int PH, int S1>
+    __device__ __forceinline__ void stage(Windows &Lv, int n, const Groups &G, const bool FAST) const {
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
         if (!FAST) {
@@ -344,13 +344,13 @@ struct SweepT {
         }
     }
 
-    template <int PH, bool FAST>
-    __device__ __forceinline__ void iteration(Windows &Lv, int n, const Groups &G) const {
-        stage<PH, 1, FAST>(Lv, n, G);
-        if constexpr (NST >= 2) stage<PH, 2, FAST>(Lv, n, G);
+    template <int PH>
+    __device__ __forceinline__ void iteration(Windows &Lv, int n, const Groups &G, const bool fast) const {
+        stage<PH, 1>(Lv, n, G, fast);
+        if constexpr (NST >= 2) stage<PH, 2>(Lv, n, G, fast);
         if constexpr (NST >= 4) {
-            stage<PH, 3, FAST>(Lv, n, G);
-            stage<PH, 4, FAST>(Lv, n, G);
+            stage<PH, 3>(Lv, n, G, fast);
+            stage<PH, 4>(Lv, n, G, fast);
         }
     }
 
@@ -375,17 +375,12 @@ struct SweepT {
             const int r_last = y0 - NST + n - NST;      // smallest center row touched in this triple
             const int r_first = y0 - NST + (n + 2) - 1; // largest
             const bool fast = !edge_strip && n >= 2 * NST && n + 2 < niter && r_last > gmin && r_first < gmax;
-            if (fast) {
-                iteration<0, true>(Lv, n, G);
-                refill(q);
-                iteration<1, true>(Lv, n + 1, G);
-                iteration<2, true>(Lv, n + 2, G);
-            } else {
-                iteration<0, false>(Lv, n, G);
-                refill(q);
-                if (n + 1 < niter) iteration<1, false>(Lv, n + 1, G);
-                if (n + 2 < niter) iteration<2, false>(Lv, n + 2, G);
-            }
+            // one code body for both cases (it has to fit the instruction cache): in the steady state the
+            // boundary tests are skipped by uniform branches
+            iteration<0>(Lv, n, G, fast);
+            refill(q);
+            if (fast || n + 1 < niter) iteration<1>(Lv, n + 1, G, fast);
+            if (fast || n + 2 < niter) iteration<2>(Lv, n + 2, G, fast);
             const T *t = G.c;  // rotate: triple q+1 lives where triple q-2 lived
             G.c = G.b;
             G.b = G.a;

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libweather_b200.so")
+# WSB_LIBRARY points at an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("WSB_LIBRARY") or os.path.join(os.path.dirname(_HERE), "lib", "libweather_b200.so")
 
 WSB_OK = 0
 WSB_ERR_INVALID_ARGUMENT = -1
