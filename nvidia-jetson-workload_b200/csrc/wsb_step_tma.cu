@@ -476,7 +476,7 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
 }  // namespace
 
 bool step_tma_supported(int nstages, int dtype) {
-    if (dtype == WSB_F64) return nstages == 1 || nstages == 2;
+    (void)dtype;  // fp32: 2 cells per lane; fp64: 1 cell per lane -- both fit the register budget at 4 stages
     return nstages == 1 || nstages == 2 || nstages == 4;
 }
 
@@ -499,6 +499,7 @@ cudaError_t launch_step_tma<double>(const Geometry<double> &g, const Physics<dou
     switch (nstages) {
         case 1: return launch_impl<double, 1, 1, 20>(g, ph, a, st);
         case 2: return launch_impl<double, 2, 1, 16>(g, ph, a, st);
+        case 4: return launch_impl<double, 4, 1, 12>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
 }

@@ -171,4 +171,4 @@ def test_python_output_manager_and_double_precision(ours):
     o.set_field("h", h)
     o.step(3)
     assert sim64.get_current_grid().get_height_field().tobytes() == o.get_field("h").tobytes()
-    assert sim64.get_kernel_name() == "stage_direct"  # fp64 RK4 has no whole-step kernel
+    assert sim64.get_kernel_name() == "step_fused_tma"
