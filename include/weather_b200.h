@@ -218,6 +218,14 @@ WSB_API int wsb_sim_initialize(wsb_sim *sim);
 WSB_API wsb_grid *wsb_sim_current_grid(wsb_sim *sim);
 /* WeatherSimulation::step (ws.cpp:117-158): one time step; time += dt (in the sim's dtype); step++. */
 WSB_API int wsb_sim_step(wsb_sim *sim);
+/* One time step with the state STREAMED through the GPU (host buffers in, host buffers out): equivalent to
+ * set_field(u,v,h) + wsb_sim_step + get_field(u,v,h), but pipelined in row slabs on three streams -- slab
+ * i+1 uploads while slab i is stepped and slab i-1 downloads -- so a host-resident step costs one PCIe
+ * direction, not two. What a user of the reference does per step when the state lives in numpy
+ * (pb.cpp:60-114 in, ws.cpp:117-158, pb.cpp:22-57 out). Buffers: (H, W) (or (L, H, W)) of the simulation's
+ * dtype, page-locked for full overlap (wsb_host_alloc). Outputs may alias the inputs. */
+WSB_API int wsb_sim_step_host(wsb_sim *sim, const void *u, const void *v, const void *h, void *out_u, void *out_v,
+                              void *out_h);
 /* WeatherSimulation::run (ws.cpp:68-103) incl. the early stop at time >= max_time. steps_done may be NULL.
  * The whole run is enqueued asynchronously and synchronised once at the end. */
 WSB_API int wsb_sim_run(wsb_sim *sim, int32_t num_steps, int32_t *steps_done);

@@ -200,6 +200,9 @@ struct wsb_sim {
     void *k3[3] = {nullptr, nullptr, nullptr};
     bool diag_dirty = false;  // vorticity/divergence need recomputing from the current u, v
     bool halo_valid = false;  // ghost rows of the current state are up to date (nranks > 1)
+    static constexpr int kMaxSlabs = 32;  // row slabs of the streamed host step
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_up[kMaxSlabs] = {}, ev_done[kMaxSlabs] = {};
     cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr, ev_interior = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
@@ -782,6 +785,16 @@ static void sim_free(wsb_sim *s) {
         if (e) cudaEventDestroy(e);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
+    if (s->h2d_stream) {
+        cudaStreamSynchronize(s->h2d_stream);
+        cudaStreamSynchronize(s->d2h_stream);
+        for (int i = 0; i < wsb_sim::kMaxSlabs; ++i) {
+            if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+            if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
+        }
+        cudaStreamDestroy(s->h2d_stream);
+        cudaStreamDestroy(s->d2h_stream);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -947,6 +960,112 @@ int wsb_sim_synchronize(wsb_sim *s) {
 int wsb_sim_step(wsb_sim *s) {
     WSB_TRY(wsb_sim_advance_async(s, 1));
     return sim_sync(s);
+}
+
+}  // extern "C"
+
+// Streamed host step: see include/weather_b200.h. Row slabs flow H2D -> whole-step kernel -> D2H on three
+// streams; slab i can be stepped up to `halo` rows short of its end as soon as it has landed.
+template <typename T>
+static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const out[3]) {
+    wsb_grid *g = &s->cur;
+    const int H = g->H, W = g->W, halo = s->nstages;
+    const size_t es = sizeof(T), row_bytes = (size_t)W * es, pitch_bytes = (size_t)g->pitch * es;
+    if (!s->h2d_stream) {
+        WSB_CUDA(cudaStreamCreateWithFlags(&s->h2d_stream, cudaStreamNonBlocking));
+        WSB_CUDA(cudaStreamCreateWithFlags(&s->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < wsb_sim::kMaxSlabs; ++i) {
+            WSB_CUDA(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+            WSB_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    const Geometry<T> geo = g->geom<T>();
+    const Physics<T> ph = g->physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    void *cur3[3] = {g->f[0].base, g->f[1].base, g->f[2].base};
+    StepArgs<T> a{};
+    a.Y = planes<const T>(s, cur3);
+    a.O = planes<T>(s, s->next);
+    a.dt = (T)s->dt;
+    a.half_dt = T(0.5f) * a.dt;
+    a.dt6 = a.dt / T(6.0f);
+    const int nslabs = std::max(1, std::min((int)wsb_sim::kMaxSlabs, H / 256));
+    const int rows_per_slab = (H + nslabs - 1) / nslabs;
+    // everything already enqueued on the main stream (previous steps) precedes the first upload
+    WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
+    WSB_CUDA(cudaStreamWaitEvent(s->h2d_stream, s->ev_edge, 0));
+    WSB_CUDA(cudaStreamWaitEvent(s->d2h_stream, s->ev_edge, 0));
+    int done_rows = 0;
+    for (int i = 0; i < nslabs; ++i) {
+        const int r0 = i * rows_per_slab, r1 = std::min(H, r0 + rows_per_slab);
+        if (r0 >= r1) break;
+        for (int l = 0; l < g->L; ++l)
+            for (int k = 0; k < 3; ++k) {
+                char *dst = (char *)g->origin(k) + ((size_t)l * g->level_stride + (size_t)r0 * g->pitch) * es;
+                const char *src = (const char *)in[k] + ((size_t)l * H + r0) * row_bytes;
+                WSB_CUDA(cudaMemcpy2DAsync(dst, pitch_bytes, src, row_bytes, row_bytes, (size_t)(r1 - r0),
+                                           cudaMemcpyHostToDevice, s->h2d_stream));
+            }
+        WSB_CUDA(cudaEventRecord(s->ev_up[i], s->h2d_stream));
+        const int end = (r1 == H) ? H : r1 - halo;  // rows whose stencil inputs have all landed
+        if (end <= done_rows) continue;
+        WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up[i], 0));
+        a.y_begin = done_rows;
+        a.y_end = end;
+        WSB_CUDA(launch_step<T>(s, geo, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+        WSB_CUDA(cudaEventRecord(s->ev_done[i], s->stream));
+        WSB_CUDA(cudaStreamWaitEvent(s->d2h_stream, s->ev_done[i], 0));
+        for (int l = 0; l < g->L; ++l)
+            for (int k = 0; k < 3; ++k) {
+                const char *src = (const char *)plane_origin(s, s->next[k]) +
+                                  ((size_t)l * g->level_stride + (size_t)done_rows * g->pitch) * es;
+                char *dst = (char *)out[k] + ((size_t)l * H + done_rows) * row_bytes;
+                WSB_CUDA(cudaMemcpy2DAsync(dst, row_bytes, src, pitch_bytes, row_bytes, (size_t)(end - done_rows),
+                                           cudaMemcpyDeviceToHost, s->d2h_stream));
+            }
+        done_rows = end;
+    }
+    // the main stream rejoins the copy streams: later work sees a complete state
+    WSB_CUDA(cudaEventRecord(s->ev_halo, s->d2h_stream));
+    WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    return WSB_OK;
+}
+
+extern "C" {
+
+int wsb_sim_step_host(wsb_sim *s, const void *u, const void *v, const void *h, void *out_u, void *out_v,
+                      void *out_h) {
+    if (!s || !u || !v || !h || !out_u || !out_v || !out_h) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    WSB_CUDA(cudaSetDevice(s->cur.device));
+    wsb_grid *g = &s->cur;
+    const bool pipelined = is_step_path(s->path) && !s->comm && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
+    if (!pipelined) {  // same result, unpipelined: upload, step, download
+        const void *in[3] = {u, v, h};
+        void *out[3] = {out_u, out_v, out_h};
+        for (int k = 0; k < 3; ++k) WSB_TRY(wsb_grid_set_field(g, k, in[k], s->dtype, g->L, g->H, g->W));
+        WSB_TRY(wsb_sim_step(s));
+        for (int k = 0; k < 3; ++k) WSB_TRY(wsb_grid_get_field(g, k, out[k], s->dtype, g->L, g->H, g->W));
+        return WSB_OK;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    WSB_TRY(sim_begin_timing(s));
+    const void *in[3] = {u, v, h};
+    void *out[3] = {out_u, out_v, out_h};
+    if (s->dtype == WSB_F64) WSB_TRY(step_host_pipelined<double>(s, in, out));
+    else WSB_TRY(step_host_pipelined<float>(s, in, out));
+    // bookkeeping of one step (sim_enqueue_step without the launch)
+    for (int k = 0; k < 3; ++k) std::swap(g->f[k].base, s->next[k]);
+    for (int k = WSB_FIELD_PRESSURE; k <= WSB_FIELD_HUMIDITY; ++k) std::swap(g->f[k], s->alt[k]);
+    s->diag_dirty = true;
+    if (s->dtype == WSB_F32) s->time = (double)((float)s->time + (float)s->dt);
+    else s->time += s->dt;
+    s->step += 1;
+    s->metrics.num_steps += 1;
+    WSB_TRY(sim_sync(s));
+    WSB_CUDA(cudaStreamSynchronize(s->h2d_stream));
+    WSB_CUDA(cudaStreamSynchronize(s->d2h_stream));
+    s->metrics.total_time_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return WSB_OK;
 }
 
 int wsb_sim_run(wsb_sim *s, int32_t num_steps, int32_t *steps_done) {

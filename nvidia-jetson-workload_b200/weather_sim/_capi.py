@@ -124,6 +124,7 @@ SIGNATURES = {
     "wsb_sim_initialize": (ctypes.c_int, [_vp]),
     "wsb_sim_current_grid": (_vp, [_vp]),
     "wsb_sim_step": (ctypes.c_int, [_vp]),
+    "wsb_sim_step_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wsb_sim_run": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i32)]),
     "wsb_sim_run_until": (ctypes.c_int, [_vp, _dbl, ctypes.POINTER(_i32)]),
     "wsb_sim_advance_async": (ctypes.c_int, [_vp, _i32]),
@@ -366,6 +367,19 @@ class Simulation:
         """n reference step() calls (no max_time check), synchronised at the end."""
         _check(self._lib.wsb_sim_advance_async(self._h, int(n)))
         _check(self._lib.wsb_sim_synchronize(self._h))
+
+    def step_host(self, u, v, h, out_u=None, out_v=None, out_h=None):
+        """One step with host-resident state: streams u, v, h through the GPU in row slabs (upload, step and
+        download overlap) and returns the new (u, v, h). Arrays must have the simulation's dtype and shape;
+        page-locked arrays (pinned_empty) give full overlap. Outputs default to new arrays."""
+        ins = [np.ascontiguousarray(a, dtype=self.dtype) for a in (u, v, h)]
+        outs = [np.empty_like(ins[0]) if o is None else o for o in (out_u, out_v, out_h)]
+        exp = self.grid.shape if self.grid.shape[0] > 1 else self.grid.shape[1:]
+        for a in ins + outs:
+            if tuple(a.shape) != tuple(exp) or a.dtype != self.dtype or not a.flags.c_contiguous:
+                raise RuntimeError("Array dimensions must match field dimensions")
+        _check(self._lib.wsb_sim_step_host(self._h, *[a.ctypes.data for a in ins], *[a.ctypes.data for a in outs]))
+        return tuple(outs)
 
     def advance_async(self, n):
         _check(self._lib.wsb_sim_advance_async(self._h, int(n)))

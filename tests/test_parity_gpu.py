@@ -361,3 +361,32 @@ def test_full_size_8192_step_fused_equals_stage_path_and_oracle_crops():
             full = res["step_fused_tma"][n][y0:y0 + C, x0:x0 + C]
             assert_bit_equal(np.ascontiguousarray(full[ys, xs]), np.ascontiguousarray(o.get_field(n)[ys, xs]),
                              f"crop ({y0},{x0}) {n}")
+
+
+# ------------------------------------------------------------------------ streamed host step --
+@pytest.mark.parametrize("integ,dtype", [(2, np.float32), (0, np.float32), (1, np.float64)])
+def test_step_host_streams_the_state_and_matches_the_oracle(integ, dtype):
+    """wsb_sim_step_host == set_field + step + get_field, pipelined in row slabs (upload / step / download
+    overlap). 1500 rows -> 5 slabs; pinned and pageable buffers; outputs aliasing the inputs."""
+    W, H = 200, 1500
+    u, v, h = (a.astype(dtype) for a in syn.random_vorticity(W, H, dtype=np.float64))
+    h = (h + syn.gaussian_bump(W, H, dtype=np.float64)[2] - 10.0).astype(dtype)
+    o = Oracle(W, H, 0, integ, dtype=dtype, coriolis_f=0.1)
+    o.set_state(u, v, h)
+    s = cuda_sim(W, H, 0, integ, "auto", dtype=dtype, coriolis_f=0.1)
+    pu, pv, ph = (_capi.pinned_empty((H, W), dtype) for _ in range(3))
+    pu[...], pv[...], ph[...] = u, v, h
+    for k in range(3):
+        o.step(1)
+        if k == 1:  # pageable in, fresh arrays out
+            ou, ov, oh = s.step_host(pu.copy(), pv.copy(), ph.copy())
+            pu[...], pv[...], ph[...] = ou, ov, oh
+        else:       # pinned, in place
+            s.step_host(pu, pv, ph, pu, pv, ph)
+        for name, got in (("u", pu), ("v", pv), ("h", ph)):
+            assert_bit_equal(np.array(got), o.get_field(name), f"step_host step {k} {name}")
+        # the device-resident state is the same thing
+        assert_bit_equal(s.get_field("h"), o.get_field("h"), "device state after step_host")
+    assert s.steps == 3 and s.time == o.time
+    assert_bit_equal(s.get_field("vorticity"), o.get_field("vorticity"), "vorticity after step_host")
+    s.close()
