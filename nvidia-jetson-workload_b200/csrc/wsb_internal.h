@@ -111,6 +111,11 @@ cudaError_t launch_diagnostics(const Geometry<T> &g, const Physics<T> &ph, const
 template <typename T>
 cudaError_t launch_axpy_const(const Geometry<T> &g, const T *y, T *o, T c, T k, cudaStream_t st);
 
+// both Primitive drifts (T and p) in one vectorised streaming pass
+template <typename T>
+cudaError_t launch_axpy_const2(const Geometry<T> &g, const T *ta, T *to, const T *pa, T *po, T c, T kt, T kp,
+                               cudaStream_t st);
+
 template <typename T>
 cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st);
 

@@ -86,6 +86,32 @@ __global__ void __launch_bounds__(kBX *kBY)
     o[i] = axpy<T>(yv[i], c, k);
 }
 
+// Both Primitive-equations drifts in one streaming pass: T' = T + c*kT and p' = p + c*kp over the
+// contiguous rows [0, H) x pitch of one level (padding columns included: they are never read back).
+// 128-bit accesses; 16 B/cell of traffic (weather_simulation.cpp:201-214, 311-319).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    axpy_const2_kernel(const Geometry<T> g, const T *__restrict__ ta, T *__restrict__ to, const T *__restrict__ pa,
+                       T *__restrict__ po, T c, T kt, T kp) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const long long n = (long long)g.H * g.pitch / VEC;  // pitch is a multiple of 128 bytes
+    const long long base = (long long)blockIdx.y * g.level_stride;
+    const T ckt = Ar<T>::mul(c, kt), ckp = Ar<T>::mul(c, kp);  // c*k once: the same product for every cell
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        alignas(16) T a[VEC];
+        alignas(16) T b[VEC];
+        *reinterpret_cast<int4 *>(a) = *reinterpret_cast<const int4 *>(ta + base + i * VEC);
+        *reinterpret_cast<int4 *>(b) = *reinterpret_cast<const int4 *>(pa + base + i * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            a[e] = Ar<T>::add(a[e], ckt);
+            b[e] = Ar<T>::add(b[e], ckp);
+        }
+        *reinterpret_cast<int4 *>(to + base + i * VEC) = *reinterpret_cast<const int4 *>(a);
+        *reinterpret_cast<int4 *>(po + base + i * VEC) = *reinterpret_cast<const int4 *>(b);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBX *kBY) fill_kernel(const Geometry<T> g, T *__restrict__ p, T value, int halo) {
     const int x = blockIdx.x * kBX + threadIdx.x;
@@ -171,6 +197,13 @@ cudaError_t launch_axpy_const(const Geometry<T> &g, const T *y, T *o, T c, T k, 
 }
 
 template <typename T>
+cudaError_t launch_axpy_const2(const Geometry<T> &g, const T *ta, T *to, const T *pa, T *po, T c, T kt, T kp,
+                               cudaStream_t st) {
+    axpy_const2_kernel<T><<<dim3(148 * 8, g.L), 256, 0, st>>>(g, ta, to, pa, po, c, kt, kp);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st) {
     const int halo = with_halo ? kHaloRows : 0;
     fill_kernel<T><<<grid_for(g, g.H + 2 * halo, g.pitch), dim3(kBX, kBY), 0, st>>>(g, p, value, halo);
@@ -190,6 +223,8 @@ cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, con
     template cudaError_t launch_diagnostics<T>(const Geometry<T> &, const Physics<T> &, const T *, const T *, T *,   \
                                                T *, cudaStream_t);                                                  \
     template cudaError_t launch_axpy_const<T>(const Geometry<T> &, const T *, T *, T, T, cudaStream_t);              \
+    template cudaError_t launch_axpy_const2<T>(const Geometry<T> &, const T *, T *, const T *, T *, T, T, T,         \
+                                               cudaStream_t);                                                       \
     template cudaError_t launch_fill<T>(const Geometry<T> &, T *, T, bool, cudaStream_t);                            \
     template cudaError_t launch_mass_energy<T>(const Geometry<T> &, const T *, const T *, const T *, double,         \
                                                double *, int, cudaStream_t);

@@ -408,16 +408,16 @@ static int enqueue_primitive_tp(wsb_sim *s) {
     const Geometry<T> g = s->cur.geom<T>();
     const int fields[2] = {WSB_FIELD_TEMPERATURE, WSB_FIELD_PRESSURE};
     for (int k = 0; k < 2; ++k) {
-        const int fld = fields[k];
-        WSB_TRY(grid_materialize(&s->cur, fld));
-        if (!s->alt[fld].base) {
-            WSB_TRY(grid_alloc_plane(&s->cur, &s->alt[fld].base));
-        }
-        const T *y = (const T *)s->cur.origin(fld);
-        T *o = (T *)plane_origin(s, s->alt[fld].base);
-        WSB_CUDA(launch_axpy_const<T>(g, y, o, (T)s->dt, (T)kResetValue[fld], s->stream));
-        s->metrics.kernel_launches += 1;
+        WSB_TRY(grid_materialize(&s->cur, fields[k]));
+        if (!s->alt[fields[k]].base) WSB_TRY(grid_alloc_plane(&s->cur, &s->alt[fields[k]].base));
     }
+    WSB_CUDA(launch_axpy_const2<T>(g, (const T *)s->cur.origin(WSB_FIELD_TEMPERATURE),
+                                   (T *)plane_origin(s, s->alt[WSB_FIELD_TEMPERATURE].base),
+                                   (const T *)s->cur.origin(WSB_FIELD_PRESSURE),
+                                   (T *)plane_origin(s, s->alt[WSB_FIELD_PRESSURE].base), (T)s->dt,
+                                   (T)kResetValue[WSB_FIELD_TEMPERATURE], (T)kResetValue[WSB_FIELD_PRESSURE],
+                                   s->stream));
+    s->metrics.kernel_launches += 1;
     return WSB_OK;
 }
 
