@@ -862,7 +862,7 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         int want = c.kernel_variant;
         const bool classical4 = s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL;
         const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4;
-        const bool tma_ok = step_tma_supported(s->nstages, s->dtype) && !classical4;
+        const bool tma_ok = step_tma_supported(s->nstages, s->dtype);  // incl. the classical RK4 opt-in
         if (want == WSB_KERNEL_AUTO)
             want = tma_ok ? WSB_KERNEL_STEP_FUSED_TMA : reg_ok ? WSB_KERNEL_STEP_FUSED_REG : WSB_KERNEL_STAGE_DIRECT;
         if (want == WSB_KERNEL_STEP_FUSED_REG || want == WSB_KERNEL_STEP_FUSED_TMA) {

@@ -93,11 +93,12 @@ struct Layout {
     static constexpr int FIELD_BYTES = SW * (int)sizeof(T);
     static constexpr int ROW_ELEMS = 3 * SW;
     static constexpr int ROW_BYTES = 3 * FIELD_BYTES;
-    static constexpr int K_ROWS = NST == 4 ? 6 : 0;                     // k2 and k3: 3 rows each
-    static constexpr int SMEM_BYTES = (kRing + K_ROWS) * ROW_BYTES + kGroups * 8;
+    // RK4 parks two 3-row rings in shared memory (k2 and k3; classical opt-in: k1, k1+2k2, k1+2k2+2k3)
+    static __host__ __device__ constexpr int k_rows(bool classical) { return NST == 4 ? (classical ? 9 : 6) : 0; }
+    static __host__ __device__ constexpr int smem_bytes(bool classical) { return (kRing + k_rows(classical)) * ROW_BYTES + kGroups * 8; }
 };
 
-template <typename T, int NST, int V, bool RECIP>
+template <typename T, int NST, int V, bool RECIP, bool CL>
 struct SweepT {
     using L = Layout<T, NST, V>;
     using Windows = Row<T, V>[(NST > 1 ? NST - 1 : 1)][3];
@@ -118,6 +119,8 @@ struct SweepT {
     T *ring;        // [kRing][3][SW]
     T *k2s;         // [3][3][SW], lane-offset
     T *k3s;         // [3][3][SW], lane-offset
+    T *k1s;         // [3][3][SW], lane-offset (classical RK4 only)
+    static constexpr bool classical = NST == 4 && CL;  // textbook RK4 opt-in: its own kernel instantiation
     uint32_t ring_u32, bar_u32;
     bool st_vec, st_e[V], ragged;
 
@@ -300,14 +303,38 @@ struct SweepT {
                     Lv[S1 - 1][m3m] = t;
                 }
             }
-            if constexpr (NST == 4 && S1 == 2) st_k(k, k2s, m3);
-            if constexpr (NST == 4 && S1 == 3) st_k(k, k3s, m3);
+            if constexpr (NST == 4) {
+                if constexpr (!classical) {
+                    if constexpr (S1 == 2) st_k(k, k2s, m3);
+                    if constexpr (S1 == 3) st_k(k, k3s, m3);
+                } else {
+                    // textbook RK4 (opt-in): carry the running sum ((k1 + 2*k2) + 2*k3) instead of k2 and k3
+                    if constexpr (S1 == 1) st_k(k, k1s, m3);
+                    if constexpr (S1 == 2 || S1 == 3) {
+                        Row<T, V> acc;
+                        ld_k(acc, S1 == 2 ? k1s : k2s, m3);
+#pragma unroll
+                        for (int f = 0; f < 3; ++f)
+#pragma unroll
+                            for (int e = 0; e < V; ++e) acc.f[f][e] = Ar<T>::add(acc.f[f][e], Ar<T>::mul(T(2), k.f[f][e]));
+                        st_k(acc, S1 == 2 ? k2s : k3s, m3);
+                    }
+                }
+            }
         } else {
             Row<T, V> o;
             if constexpr (NST == 4) {
                 Row<T, V> k2, k3;
-                ld_k(k2, k2s, m3);
                 ld_k(k3, k3s, m3);
+                if constexpr (classical) {
+                    // y + dt6 * ((((k1 + 2*k2) + 2*k3)) + k4), the sum so far is in the k3 ring
+#pragma unroll
+                    for (int f = 0; f < 3; ++f)
+#pragma unroll
+                        for (int e = 0; e < V; ++e)
+                            o.f[f][e] = Ar<T>::add(yb.f[f][e], Ar<T>::mul(a.dt6, Ar<T>::add(k3.f[f][e], k.f[f][e])));
+                } else {
+                ld_k(k2, k2s, m3);
                 // reference aliasing: "k1" reads k4 at the combine (weather_simulation.cpp:350-351, F5)
                 if constexpr (kPacked) {
                     const F2 dt6 = f2_splat((float)a.dt6);
@@ -325,6 +352,7 @@ struct SweepT {
 #pragma unroll
                         for (int e = 0; e < V; ++e)
                             o.f[f][e] = rk4_combine<T>(yb.f[f][e], a.dt6, k.f[f][e], k2.f[f][e], k3.f[f][e], k.f[f][e]);
+                }
                 }
             } else if constexpr (kPacked) {
                 const F2 dt2 = f2_splat((float)a.dt);
@@ -389,7 +417,7 @@ struct SweepT {
     }
 };
 
-template <typename T, int NST, int V, bool RECIP, int MINB>
+template <typename T, int NST, int V, bool RECIP, int MINB, bool CL>
 __global__ void __launch_bounds__(32, MINB)
     step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk) {
     using L = Layout<T, NST, V>;
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(32, MINB)
     const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
     if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform
 
-    SweepT<T, NST, V, RECIP> sw(g, ph, a);
+    SweepT<T, NST, V, RECIP, CL> sw(g, ph, a);
     sw.ph2.rdx = f2_splat((float)ph.rdx);
     sw.ph2.rdy = f2_splat((float)ph.rdy);
     sw.ph2.g = f2_splat((float)ph.g);
@@ -425,8 +453,9 @@ __global__ void __launch_bounds__(32, MINB)
     sw.ring = reinterpret_cast<T *>(smem_raw);
     sw.k2s = sw.ring + kRing * L::ROW_ELEMS + lane * V;
     sw.k3s = sw.k2s + 3 * L::ROW_ELEMS;
+    sw.k1s = sw.k3s + 3 * L::ROW_ELEMS;
     sw.ring_u32 = smem_u32(sw.ring);
-    sw.bar_u32 = smem_u32(smem_raw + (kRing + L::K_ROWS) * L::ROW_BYTES);
+    sw.bar_u32 = smem_u32(smem_raw + (kRing + L::k_rows(NST == 4 && CL)) * L::ROW_BYTES);
     bool all_in = true;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
@@ -468,8 +497,15 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk : rows_per_chunk_default();
     const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
     const dim3 grid(strips, chunks, g.L);
-    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
-    else step_tma_kernel<T, NST, V, false, MINB><<<grid, 32, L::SMEM_BYTES, st>>>(g, ph, a, rpc);
+    if constexpr (NST == 4) {
+        if (a.classical) {  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
+            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc);
+            else step_tma_kernel<T, NST, V, false, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc);
+            return cudaGetLastError();
+        }
+    }
+    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc);
+    else step_tma_kernel<T, NST, V, false, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc);
     return cudaGetLastError();
 }
 
@@ -483,7 +519,6 @@ bool step_tma_supported(int nstages, int dtype) {
 template <>
 cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float> &ph, const StepArgs<float> &a,
                                    int nstages, cudaStream_t st) {
-    if (a.classical && nstages == 4) return cudaErrorNotSupported;
     switch (nstages) {
         case 1: return launch_impl<float, 1, 2, 20>(g, ph, a, st);
         case 2: return launch_impl<float, 2, 2, 16>(g, ph, a, st);
@@ -495,7 +530,6 @@ cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float
 template <>
 cudaError_t launch_step_tma<double>(const Geometry<double> &g, const Physics<double> &ph, const StepArgs<double> &a,
                                     int nstages, cudaStream_t st) {
-    if (a.classical && nstages == 4) return cudaErrorNotSupported;
     switch (nstages) {
         case 1: return launch_impl<double, 1, 1, 20>(g, ph, a, st);
         case 2: return launch_impl<double, 2, 1, 16>(g, ph, a, st);

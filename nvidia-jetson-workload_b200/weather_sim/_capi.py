@@ -232,6 +232,14 @@ def _np_dtype(code):
     return np.float64 if code == WSB_F64 else np.float32
 
 
+class DeviceField:
+    """Holder of a `__cuda_array_interface__` dict; keeps the owning grid alive."""
+
+    def __init__(self, iface, owner):
+        self.__cuda_array_interface__ = iface
+        self._owner = owner
+
+
 class Grid:
     """Device-resident WeatherGrid (weather_sim.hpp:254-412). Getters return fresh host copies."""
 
@@ -287,6 +295,21 @@ class Grid:
         _check(self._lib.wsb_grid_get_field(self._h, FIELD[name], out.ctypes.data, code, gi.num_levels, gi.height,
                                             gi.width))
         return out
+
+    def device_view(self, name):
+        """Zero-copy view of a field in HBM: an object exposing
+        `__cuda_array_interface__` (version 3) that cupy.asarray / torch.as_tensor wrap without a copy. Rows are
+        pitched (128-byte aligned); the view is valid until the next step() (the u, v, h planes rotate)."""
+        ptr, pitch = ctypes.c_void_p(), ctypes.c_int64()
+        _check(self._lib.wsb_grid_device_pointer(self._h, FIELD[name], ctypes.byref(ptr), ctypes.byref(pitch)))
+        gi = self.info
+        es = 8 if gi.dtype == WSB_F64 else 4
+        lead = 5  # rows between consecutive levels beyond H: 2 * (4 ghost + 1 guard), see DESIGN.md section 3
+        shape = (gi.height, gi.width) if gi.num_levels == 1 else (gi.num_levels, gi.height, gi.width)
+        strides = (pitch.value * es, es) if gi.num_levels == 1 else \
+            ((gi.height + 2 * lead) * pitch.value * es, pitch.value * es, es)
+        return DeviceField({"shape": shape, "typestr": "<f8" if es == 8 else "<f4", "data": (ptr.value, False),
+                            "version": 3, "strides": strides}, self)
 
     def reset(self):
         _check(self._lib.wsb_grid_reset(self._h))
