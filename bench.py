@@ -342,7 +342,15 @@ def run_b200_arm(args, wl, rank, world, local_rank):
         if e2e is not None:
             line["e2e"] = e2e
         if world > 1:
-            line["halo_ms_last_exchange"] = sim.metrics.halo_time_ms
+            # ghost rows: `stages` rows x 3 fields per neighbour per step, one ncclSend/ncclRecv group
+            stages = {"euler": 1, "rk2": 2, "rk4": 4 if wl["model"] == "shallow_water" else 2}[wl["integ"]]
+            hb_bytes = stages * 3 * W * esize
+            line["halo"] = {"bytes_per_neighbour_per_step": hb_bytes,
+                            "nvlink_bound_us": hb_bytes / 770e9 * 1e6,
+                            "measured_last_exchange_ms": sim.metrics.halo_time_ms,
+                            "note": "bound = bytes / 770 GB/s (measured peer copy rate); the exchange is latency- and "
+                                    "skew-bound (it waits for the neighbour's edge band), and it runs on its own "
+                                    "stream beside the interior sweep"}
         if world == 1 and not args.no_cpu_baseline:
             n = 2048 if wl["integ"] != "euler" else 4096
             steps = 20
