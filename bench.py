@@ -35,6 +35,10 @@ UNIT = "cell-updates/s"
 # bpc_stage / bpc_step: algorithmic bytes per cell per step of a one-pass-per-RK-stage
 # design and of the whole-step kernels (read y_n once, write y_n+1 once; + T,p read/write for Primitive).
 WORKLOADS = {
+    # schema/self-test size (tests/test_bench_gpu.py), not a benchmark
+    "tiny_swe512_rk4": dict(W=512, rows=512, model="shallow_water", integ="rk4", dtype="f32", levels=1,
+                            scaling="weak", metric="grid cell-updates/sec (RK4 SWE step)",
+                            desc="SWE {W}x{H} fp32 RK4 (self-test size)", bpc_stage=168, bpc_step=24),
     "swe8192_rk4": dict(W=8192, rows=8192, model="shallow_water", integ="rk4", dtype="f32", levels=1,
                         scaling="weak", metric="grid cell-updates/sec (RK4 SWE step)",
                         desc="SWE {W}x{H} fp32 RK4 (reference-parity combine)", bpc_stage=168, bpc_step=24),
@@ -352,8 +356,8 @@ def run_b200_arm(args, wl, rank, world, local_rank):
                                     "skew-bound (it waits for the neighbour's edge band), and it runs on its own "
                                     "stream beside the interior sweep"}
         if world == 1 and not args.no_cpu_baseline:
-            n = 2048 if wl["integ"] != "euler" else 4096
-            steps = 20
+            n = min(wl["rows"], 2048 if wl["integ"] != "euler" else 4096)
+            steps = 20 if wl["rows"] >= 2048 else 3
             r = time_reference_cpu(n, n, steps, 2, MODEL_CODE[wl["model"]], INTEG_CODE[wl["integ"]])
             line["cpu_baseline"] = {
                 "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],

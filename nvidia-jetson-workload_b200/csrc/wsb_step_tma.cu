@@ -522,7 +522,7 @@ cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float
     switch (nstages) {
         case 1: return launch_impl<float, 1, 2, 20>(g, ph, a, st);
         case 2: return launch_impl<float, 2, 2, 16>(g, ph, a, st);
-        case 4: return launch_impl<float, 4, 2, 20>(g, ph, a, st);
+        case 4: return launch_impl<float, 4, 2, 18>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
 }
