@@ -221,6 +221,15 @@ def run_b200_arm(args, wl, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
 
+    def all_ranks(x):
+        if dist is None:
+            return [x]
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def max_over_ranks(x):
         if dist is None:
             return x
@@ -261,6 +270,7 @@ def run_b200_arm(args, wl, rank, world, local_rank):
     barrier()
     launches = sim.metrics.kernel_launches - launches0
     ms = max_over_ranks(dev_ms)
+    ms_ranks = all_ranks(dev_ms)
     cells_total = W * H_global * L
     cells_rank = W * nrows * L
     value = cells_total * args.steps / (ms * 1e-3)
@@ -346,6 +356,7 @@ def run_b200_arm(args, wl, rank, world, local_rank):
         if e2e is not None:
             line["e2e"] = e2e
         if world > 1:
+            line["ms_per_step_per_rank"] = [m / args.steps for m in ms_ranks]
             # ghost rows: `stages` rows x 3 fields per neighbour per step, one ncclSend/ncclRecv group
             stages = {"euler": 1, "rk2": 2, "rk4": 4 if wl["model"] == "shallow_water" else 2}[wl["integ"]]
             hb_bytes = stages * 3 * W * esize

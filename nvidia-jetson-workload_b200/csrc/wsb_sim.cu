@@ -35,6 +35,13 @@ int cuda_fail(cudaError_t err, const char *what, const char *file, int line) {
 
 static inline size_t elem_size(int dtype) { return dtype == WSB_F64 ? sizeof(double) : sizeof(float); }
 
+// rows x width_bytes between a dense host array and pitched device rows; one flat copy when the pitch is dense
+static inline cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                                    size_t rows, cudaMemcpyKind kind, cudaStream_t st) {
+    if (dpitch == width_bytes && spitch == width_bytes) return cudaMemcpyAsync(dst, src, width_bytes * rows, kind, st);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, kind, st);
+}
+
 // reset() defaults, weather_grid.cpp:57-71. The float literals are the reference's; for WSB_F64 they are
 // the same float values widened (what `std::fill(..., 288.15f)` would store in a vector<double>).
 static const float kResetValue[WSB_NUM_FIELDS] = {0.0f, 0.0f, 10.0f, 1013.25f, 288.15f, 0.0f, 0.0f, 0.0f};
@@ -656,7 +663,7 @@ int wsb_grid_set_field(wsb_grid *g, int32_t field, const void *host, int32_t hos
     for (int64_t l = 0; l < levels; ++l) {
         char *dst = (char *)g->origin(field) + (size_t)l * g->level_stride * es;
         const char *s = (const char *)src + (size_t)l * rows * cols * es;
-        WSB_CUDA(cudaMemcpy2DAsync(dst, (size_t)g->pitch * es, s, (size_t)cols * es, (size_t)cols * es, (size_t)rows,
+        WSB_CUDA(copy_rows(dst, (size_t)g->pitch * es, s, (size_t)cols * es, (size_t)cols * es, (size_t)rows,
                                    cudaMemcpyHostToDevice, g->stream));
     }
     WSB_CUDA(cudaEventRecord(g->ev1, g->stream));
@@ -697,7 +704,7 @@ int wsb_grid_get_field(wsb_grid *g, int32_t field, void *host, int32_t host_dtyp
     for (int64_t l = 0; l < levels; ++l) {
         const char *s = (const char *)g->origin(field) + (size_t)l * g->level_stride * es;
         char *d = (char *)dst + (size_t)l * rows * cols * es;
-        WSB_CUDA(cudaMemcpy2DAsync(d, (size_t)cols * es, s, (size_t)g->pitch * es, (size_t)cols * es, (size_t)rows,
+        WSB_CUDA(copy_rows(d, (size_t)cols * es, s, (size_t)g->pitch * es, (size_t)cols * es, (size_t)rows,
                                    cudaMemcpyDeviceToHost, g->stream));
     }
     WSB_CUDA(cudaEventRecord(g->ev1, g->stream));
@@ -1002,7 +1009,7 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
             for (int k = 0; k < 3; ++k) {
                 char *dst = (char *)g->origin(k) + ((size_t)l * g->level_stride + (size_t)r0 * g->pitch) * es;
                 const char *src = (const char *)in[k] + ((size_t)l * H + r0) * row_bytes;
-                WSB_CUDA(cudaMemcpy2DAsync(dst, pitch_bytes, src, row_bytes, row_bytes, (size_t)(r1 - r0),
+                WSB_CUDA(copy_rows(dst, pitch_bytes, src, row_bytes, row_bytes, (size_t)(r1 - r0),
                                            cudaMemcpyHostToDevice, s->h2d_stream));
             }
         WSB_CUDA(cudaEventRecord(s->ev_up[i], s->h2d_stream));
@@ -1020,7 +1027,7 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
                 const char *src = (const char *)plane_origin(s, s->next[k]) +
                                   ((size_t)l * g->level_stride + (size_t)done_rows * g->pitch) * es;
                 char *dst = (char *)out[k] + ((size_t)l * H + done_rows) * row_bytes;
-                WSB_CUDA(cudaMemcpy2DAsync(dst, row_bytes, src, pitch_bytes, row_bytes, (size_t)(end - done_rows),
+                WSB_CUDA(copy_rows(dst, row_bytes, src, pitch_bytes, row_bytes, (size_t)(end - done_rows),
                                            cudaMemcpyDeviceToHost, s->d2h_stream));
             }
         done_rows = end;
