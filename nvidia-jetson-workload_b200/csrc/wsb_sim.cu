@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -550,7 +551,7 @@ int wsb_device_capabilities(int device_id, wsb_device_caps *out) {
     else if (p.major >= 8) out->device_type = 4;
     else out->device_type = 5;
     out->compute_power_ratio = (float)out->cuda_cores * (float)out->clock_rate_khz / (8.0f * 3.0e6f * 16.0f);
-    std::strncpy(out->device_name, p.name, sizeof(out->device_name) - 1);
+    std::snprintf(out->device_name, sizeof(out->device_name), "%s", p.name);
     return WSB_OK;
 }
 

@@ -98,3 +98,21 @@ def test_product_does_not_link_or_import_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(d, f), errors="ignore").read()
                 assert "oracle_py" not in src and "libws_oracle" not in src and "ws_ref" not in src, f
+
+
+def test_header_is_valid_c_and_the_c_example_links():
+    """include/weather_b200.h must be consumable by a C compiler (no C++-isms); the plain-C example is the
+    reference's benchmark loop on the C-ABI and has to build against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "weather_b200.h")
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "nvidia-jetson-workload_b200"), "example"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = os.path.join(ROOT, "nvidia-jetson-workload_b200", "build", "swe_example")
+    assert os.path.exists(exe)
+    if _capi.device_count() == 0:  # fails loudly, no CPU fallback
+        r = subprocess.run([exe, "64", "64", "2"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
