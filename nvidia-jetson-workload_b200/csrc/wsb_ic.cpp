@@ -26,15 +26,16 @@ struct Params {
 };
 
 struct HostFields {
-    int W, H;
+    int W, H;          // full grid extent (the formulas normalise by it)
+    int ys, ye;        // rows [ys, ye) are evaluated; the buffers hold exactly those rows
     float *u, *v, *h, *p, *t, *q;  // any may be null: that field is left untouched
     void set_uv(int x, int y, float uu, float vv) const {
-        const size_t i = (size_t)y * W + x;
+        const size_t i = (size_t)(y - ys) * W + x;
         if (u) u[i] = uu;
         if (v) v[i] = vv;
     }
     void set(float *f, int x, int y, float val) const {
-        if (f) f[(size_t)y * W + x] = val;
+        if (f) f[(size_t)(y - ys) * W + x] = val;
     }
 };
 
@@ -44,7 +45,7 @@ enum { F_U = 1, F_V = 2, F_H = 4, F_P = 8, F_T = 16, F_Q = 32 };
 int ic_uniform(const Params &a, const HostFields &g) {  // initial_conditions.cpp:59-90
     const float u = a.get(0, 0.0f), v = a.get(1, 0.0f), h = a.get(2, 10.0f), p = a.get(3, 1000.0f),
                 t = a.get(4, 300.0f), q = a.get(5, 0.0f);
-    for (int y = 0; y < g.H; ++y)
+    for (int y = g.ys; y < g.ye; ++y)
         for (int x = 0; x < g.W; ++x) {
             g.set_uv(x, y, u, v);
             g.set(g.h, x, y, h);
@@ -55,12 +56,12 @@ int ic_uniform(const Params &a, const HostFields &g) {  // initial_conditions.cp
     return F_U | F_V | F_H | F_P | F_T | F_Q;
 }
 
-int ic_random(const Params &a, uint32_t seed, const HostFields &g) {  // :98-125
-    // the reference keeps the seed as int through to_string/stoi (exact) and draws u, v, h in that order
+int ic_random(const Params &a, std::mt19937 &rng, const HostFields &g) {  // :98-125
+    // the reference seeds std::mt19937 with the int seed and draws u, v, h per cell in row-major order; the
+    // generator is carried across row blocks so that blockwise evaluation draws the same sequence
     const float amplitude = a.get(0, 1.0f);
-    std::mt19937 rng(static_cast<int>(seed));
     std::uniform_real_distribution<float> dist(-amplitude, amplitude);
-    for (int y = 0; y < g.H; ++y)
+    for (int y = g.ys; y < g.ye; ++y)
         for (int x = 0; x < g.W; ++x) {
             const float u = dist(rng);
             const float v = dist(rng);
@@ -73,7 +74,7 @@ int ic_random(const Params &a, uint32_t seed, const HostFields &g) {  // :98-125
 
 int ic_zonal_flow(const Params &a, const HostFields &g) {  // :136-177
     const float u_max = a.get(0, 10.0f), h_mean = a.get(1, 10.0f), beta = a.get(2, 0.1f);
-    for (int y = 0; y < g.H; ++y) {
+    for (int y = g.ys; y < g.ye; ++y) {
         const float y_norm = static_cast<float>(y) / (g.H - 1);
         const float u = u_max * std::sin(M_PI * y_norm);  // double product, rounded once on assignment
         for (int x = 0; x < g.W; ++x) {
@@ -91,7 +92,7 @@ int ic_vortex(const Params &a, const HostFields &g) {  // :190-240
                 strength = a.get(3, 10.0f), h_mean = a.get(4, 10.0f);
     const float xc = x_center * (g.W - 1), yc = y_center * (g.H - 1);
     const float rg = radius * std::min(g.W, g.H);
-    for (int y = 0; y < g.H; ++y)
+    for (int y = g.ys; y < g.ye; ++y)
         for (int x = 0; x < g.W; ++x) {
             const float dx = x - xc, dy = y - yc;
             const float r = std::sqrt(dx * dx + dy * dy);
@@ -114,7 +115,7 @@ int ic_jet_stream(const Params &a, const HostFields &g) {  // :252-290
                 h_mean = a.get(3, 10.0f);
     const float yc = y_center * (g.H - 1);
     const float wg = width * g.H;
-    for (int y = 0; y < g.H; ++y) {
+    for (int y = g.ys; y < g.ye; ++y) {
         const float dy = y - yc;
         const float u = strength * std::exp(-(dy * dy) / (2.0f * wg * wg));
         const float dh_dy = -1.0e-4f * u / 9.81f;
@@ -129,7 +130,7 @@ int ic_jet_stream(const Params &a, const HostFields &g) {  // :252-290
 int ic_breaking_wave(const Params &a, const HostFields &g) {  // :301-343
     const float amplitude = a.get(0, 1.0f), wavelength = a.get(1, 0.2f), h_mean = a.get(2, 10.0f);
     const float wave_k = 2.0f * M_PI / (wavelength * g.W);
-    for (int y = 0; y < g.H; ++y) {
+    for (int y = g.ys; y < g.ye; ++y) {
         const float y_norm = static_cast<float>(y) / (g.H - 1);
         const float u_base = 5.0f * std::sin(M_PI * y_norm);
         for (int x = 0; x < g.W; ++x) {
@@ -151,7 +152,7 @@ int ic_front(const Params &a, const HostFields &g) {  // :356-395
                 wind_shear = a.get(3, 5.0f);
     const float yp = y_position * (g.H - 1);
     const float wg = width * g.H;
-    for (int y = 0; y < g.H; ++y) {
+    for (int y = g.ys; y < g.ye; ++y) {
         const float dy = y - yp;
         const float tt = std::tanh(dy / wg);
         const float temperature = 288.15f + 0.5f * temp_difference * tt;
@@ -170,7 +171,7 @@ int ic_mountain(const Params &a, const HostFields &g) {  // :408-467
                 mountain_height = a.get(3, 1.0f), u_base = a.get(4, 5.0f);
     const float xc = x_center * (g.W - 1), yc = y_center * (g.H - 1);
     const float rg = radius * std::min(g.W, g.H);
-    for (int y = 0; y < g.H; ++y)
+    for (int y = g.ys; y < g.ye; ++y)
         for (int x = 0; x < g.W; ++x) {
             const float dx = x - xc, dy = y - yc;
             const float r = std::sqrt(dx * dx + dy * dy);
@@ -214,7 +215,7 @@ int ic_atmospheric_profile(const char *profile, const HostFields &g) {  // :474-
     const std::string name = profile ? profile : "standard";
     const Profile &pr = name == "tropical" ? kTropical : name == "polar" ? kPolar : kStandard;
     const size_t n = 10;
-    for (int y = 0; y < g.H; ++y) {
+    for (int y = g.ys; y < g.ye; ++y) {
         const float y_norm = static_cast<float>(y) / (g.H - 1);
         size_t idx = static_cast<size_t>(y_norm * (n - 1));
         idx = std::min(idx, n - 1);
@@ -234,10 +235,10 @@ int ic_atmospheric_profile(const char *profile, const HostFields &g) {  // :474-
 }
 
 // returns the written-field mask, or -1 for an unknown name
-int ic_dispatch(const char *name, const Params &a, uint32_t seed, const char *profile, const HostFields &g) {
+int ic_dispatch(const char *name, const Params &a, std::mt19937 &rng, const char *profile, const HostFields &g) {
     const std::string n = name ? name : "";
     if (n == "uniform") return ic_uniform(a, g);
-    if (n == "random") return ic_random(a, seed, g);
+    if (n == "random") return ic_random(a, rng, g);
     if (n == "zonal_flow") return ic_zonal_flow(a, g);
     if (n == "vortex") return ic_vortex(a, g);
     if (n == "jet_stream") return ic_jet_stream(a, g);
@@ -263,8 +264,9 @@ int wsb_ic_fill_host(const char *name, const double *params, int32_t nparams, ui
     if (width <= 0 || height <= 0) return wsb::fail(WSB_ERR_INVALID_ARGUMENT, "Grid dimensions must be positive");
     if (nparams < 0 || (nparams > 0 && !params)) return wsb::fail(WSB_ERR_INVALID_ARGUMENT, "bad parameter list");
     const Params a{params, nparams};
-    const HostFields g{width, height, u, v, h, p, t, q};
-    if (ic_dispatch(name, a, seed, profile, g) < 0)
+    const HostFields g{width, height, 0, height, u, v, h, p, t, q};
+    std::mt19937 rng(static_cast<int>(seed));
+    if (ic_dispatch(name, a, rng, profile, g) < 0)
         return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
     return WSB_OK;
 }
@@ -272,31 +274,32 @@ int wsb_ic_fill_host(const char *name, const double *params, int32_t nparams, ui
 int wsb_ic_apply(wsb_grid *grid, const char *name, const double *params, int32_t nparams, uint32_t seed,
                  const char *profile) {
     if (!grid) return wsb::fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
+    if (nparams < 0 || (nparams > 0 && !params)) return wsb::fail(WSB_ERR_INVALID_ARGUMENT, "bad parameter list");
     wsb_grid_info gi;
     WSB_TRY(wsb_grid_get_info(grid, &gi));
-    const size_t n = (size_t)gi.width * gi.height;
-    // start from the grid's current values so that fields an initial condition leaves alone keep them
-    std::vector<float> buf[6];
+    const Params a{params, nparams};
+    // a row slab of a decomposed simulation evaluates ITS rows of the global initial condition
+    int row0 = 0, Hglobal = gi.height;
+    wsb::grid_slab_position(grid, &row0, &Hglobal);
+    std::mt19937 rng(static_cast<int>(seed));
+    rng.discard(3ULL * (unsigned long long)row0 * (unsigned long long)gi.width);  // "random": 3 draws per cell
+    // Evaluate and upload in row blocks: host memory stays bounded (a 32768^2 grid is 4 GiB per field) and
+    // fields an initial condition does not write are neither allocated nor touched on the device.
+    const int block = std::max(1, std::min(gi.height, (int)(((size_t)32 << 20) / sizeof(float) / (size_t)gi.width)));
     const int fields[6] = {WSB_FIELD_U, WSB_FIELD_V, WSB_FIELD_HEIGHT, WSB_FIELD_PRESSURE, WSB_FIELD_TEMPERATURE,
                            WSB_FIELD_HUMIDITY};
-    for (auto &b : buf) b.resize(n);
-    const Params a{params, nparams};
-    const HostFields g{gi.width, gi.height, buf[0].data(), buf[1].data(), buf[2].data(),
-                       buf[3].data(), buf[4].data(), buf[5].data()};
-    const int mask = ic_dispatch(name, a, seed, profile, g);
-    if (mask < 0)
-        return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
-    // every level receives the same 2-D initial condition (the reference has a single level)
-    std::vector<float> stacked;
-    for (int k = 0; k < 6; ++k) {
-        if (!(mask & (1 << k))) continue;
-        const float *src = buf[k].data();
-        if (gi.num_levels > 1) {
-            stacked.resize(n * gi.num_levels);
-            for (int l = 0; l < gi.num_levels; ++l) std::memcpy(stacked.data() + (size_t)l * n, buf[k].data(), n * sizeof(float));
-            src = stacked.data();
-        }
-        WSB_TRY(wsb_grid_set_field(grid, fields[k], src, WSB_F32, gi.num_levels, gi.height, gi.width));
+    std::vector<float> buf[6];
+    for (auto &b : buf) b.resize((size_t)block * gi.width);
+    for (int ys = 0; ys < gi.height; ys += block) {
+        const int ye = std::min(gi.height, ys + block);
+        const HostFields g{gi.width, Hglobal, row0 + ys, row0 + ye, buf[0].data(), buf[1].data(), buf[2].data(),
+                           buf[3].data(), buf[4].data(), buf[5].data()};
+        const int mask = ic_dispatch(name, a, rng, profile, g);
+        if (mask < 0)
+            return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
+        for (int k = 0; k < 6; ++k)
+            if (mask & (1 << k))  // every level receives the same 2-D initial condition (the reference has one level)
+                WSB_TRY(wsb::grid_upload_rows(grid, fields[k], buf[k].data(), ys, ye - ys));
     }
     // every reference initial condition ends with grid.calculateDiagnostics()
     return wsb_grid_calculate_diagnostics(grid);

@@ -136,6 +136,12 @@ cudaError_t launch_step_tma(const Geometry<T> &g, const Physics<T> &ph, const St
                             cudaStream_t st);
 bool step_tma_supported(int nstages, int dtype);
 
+// rows [y0, y0+nrows) of a field from a dense float host block (nrows x W), replicated to every level and
+// converted to the grid's dtype (wsb_sim.cu; used by the blockwise initial conditions)
+int grid_upload_rows(wsb_grid *grid, int field, const float *host_rows, int y0, int nrows);
+// where this grid sits in the global domain (row slab of a decomposed simulation; else 0 and its own height)
+void grid_slab_position(const wsb_grid *grid, int *row0, int *global_height);
+
 // ---- NCCL, loaded lazily with dlopen (wsb_nccl.cpp) -------------------------------------------
 struct NcclApi;
 int nccl_load(const NcclApi **api);

@@ -508,6 +508,39 @@ static int sim_materialize_diagnostics(wsb_sim *s) {
     return wsb_grid_calculate_diagnostics(g);
 }
 
+namespace wsb {
+
+void grid_slab_position(const wsb_grid *g, int *row0, int *global_height) {
+    *row0 = g->row0;
+    *global_height = g->Hglobal;
+}
+
+int grid_upload_rows(wsb_grid *g, int field, const float *host_rows, int y0, int nrows) {
+    if (!g || !host_rows || field < 0 || field > WSB_FIELD_HUMIDITY || y0 < 0 || nrows <= 0 || y0 + nrows > g->H)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "bad row block");
+    WSB_CUDA(cudaSetDevice(g->device));
+    if (g->owner && field <= WSB_FIELD_V) WSB_TRY(sim_materialize_diagnostics(g->owner));
+    WSB_TRY(grid_materialize(g, field));
+    const size_t es = elem_size(g->dtype), n = (size_t)nrows * g->W;
+    const void *src = host_rows;
+    std::vector<double> wide;
+    if (g->dtype == WSB_F64) {
+        wide.resize(n);
+        for (size_t i = 0; i < n; ++i) wide[i] = (double)host_rows[i];
+        src = wide.data();
+    }
+    for (int l = 0; l < g->L; ++l) {
+        char *dst = (char *)g->origin(field) + ((size_t)l * g->level_stride + (size_t)y0 * g->pitch) * es;
+        WSB_CUDA(copy_rows(dst, (size_t)g->pitch * es, src, (size_t)g->W * es, (size_t)g->W * es, (size_t)nrows,
+                           cudaMemcpyHostToDevice, g->stream));
+    }
+    WSB_CUDA(cudaStreamSynchronize(g->stream));  // the caller reuses its block buffer
+    if (g->owner && field <= WSB_FIELD_HEIGHT) g->owner->halo_valid = false;
+    return WSB_OK;
+}
+
+}  // namespace wsb
+
 // ------------------------------------------------------------------------------ C-ABI: misc --
 extern "C" {
 

@@ -311,6 +311,13 @@ class Grid:
         return DeviceField({"shape": shape, "typestr": "<f8" if es == 8 else "<f4", "data": (ptr.value, False),
                             "version": 3, "strides": strides}, self)
 
+    def apply_ic(self, name, params=(), seed=0, profile=None):
+        """InitialCondition::initialize(grid) of the reference (initial_conditions.cpp:59-535) by name; params in
+        constructor order. On a row slab it evaluates this rank's rows of the global initial condition."""
+        arr = (ctypes.c_double * max(len(params), 1))(*params)
+        _check(self._lib.wsb_ic_apply(self._h, name.encode(), arr, len(params), int(seed),
+                                      profile.encode() if profile else None))
+
     def reset(self):
         _check(self._lib.wsb_grid_reset(self._h))
 

@@ -27,6 +27,7 @@ def _worker(rank, world, port, cases, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     from oracle_py import Oracle
+    from weather_sim import _capi
     from weather_sim import distributed as wd
     from weather_sim import synthetic as syn
 
@@ -55,6 +56,24 @@ def _worker(rank, world, port, cases, out_q):
                         msgs.append(f"{W}x{H} integ{integ} {kernel} {dtype} field {k}: differs "
                                     f"({int((a != b).sum())} cells)")
                 o.close()
+        # initial conditions on slabs: each rank evaluates ITS rows of the global field (incl. the sequential RNG)
+        import ctypes
+        W, H = 96, 61
+        for name, params, seed in (("vortex", (0.4, 0.6, 0.2, 5.0, 10.0), 0), ("random", (0.5,), 42), ("front", (), 0)):
+            sim = wd.slab_simulation(W, H, rank, world, device_id=rank, integrator=0, max_time=1e30)
+            sim.grid.apply_ic(name, params, seed)
+            got = {k: wd.gather_rows(sim.get_field(k), 0) for k in ("u", "v", "h", "t")}
+            sim.close()
+            if rank == 0:
+                want = {k: np.full((H, W), np.nan, np.float32) for k in "uvhptq"}
+                arr = (ctypes.c_double * max(len(params), 1))(*params)
+                st = _capi.load_library().wsb_ic_fill_host(name.encode(), arr, len(params), seed, None, W, H, 1.0, 1.0,
+                                                           *[want[k].ctypes.data for k in "uvhptq"])
+                assert st == 0
+                for k in got:
+                    ref = want[k] if not np.isnan(want[k]).all() else np.full((H, W), {"h": 10.0, "t": 288.15}.get(k, 0.0), np.float32)
+                    if got[k].tobytes() != ref.tobytes():
+                        msgs.append(f"slab initial condition {name} field {k} differs")
         out_q.put(("ok" if not msgs else "; ".join(msgs), rank))
     except Exception as e:  # pragma: no cover
         import traceback
