@@ -131,13 +131,29 @@ struct SweepT {
         : g(g_), ph(ph_), a(a_) {}
 
     // ---- producer side (lane 0): one group = 3 consecutive rows, one mbarrier -------------------------
-    __device__ __forceinline__ void issue_group(int q) const {
+    __device__ __forceinline__ void issue_group(int q, int grp) const {
         const int m0 = 3 * q;
         const int nr = min(3, niter - m0);
         if (nr <= 0) return;
-        const int grp = q % kGroups;
         const uint32_t bar = bar_u32 + 8u * grp;
         mbar_expect_tx(bar, (uint32_t)nr * L::ROW_BYTES);
+        const int r0 = y0 - NST + m0;
+        if (nr == 3 && r0 >= gmin && r0 + 2 < gmax) {
+            // common case: three consecutive in-domain rows -- one base address per field, then a stride
+            const long long off = lvl_off + (long long)r0 * g.pitch + xs;
+            const size_t pitch_bytes = (size_t)g.pitch * sizeof(T);
+            const char *pu = reinterpret_cast<const char *>(a.Y.u + off);
+            const char *pv = reinterpret_cast<const char *>(a.Y.v + off);
+            const char *ph_ = reinterpret_cast<const char *>(a.Y.h + off);
+            const uint32_t dst = ring_u32 + (uint32_t)(grp * 3) * L::ROW_BYTES;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                bulk_g2s(dst + i * L::ROW_BYTES, pu + i * pitch_bytes, L::FIELD_BYTES, bar);
+                bulk_g2s(dst + i * L::ROW_BYTES + L::FIELD_BYTES, pv + i * pitch_bytes, L::FIELD_BYTES, bar);
+                bulk_g2s(dst + i * L::ROW_BYTES + 2 * L::FIELD_BYTES, ph_ + i * pitch_bytes, L::FIELD_BYTES, bar);
+            }
+            return;
+        }
         for (int i = 0; i < nr; ++i) {
             int r = y0 - NST + m0 + i;
             r = max(r, gmin);
@@ -151,9 +167,8 @@ struct SweepT {
     }
 
     // ---- consumer side ------------------------------------------------------------------------------
-    __device__ __forceinline__ void wait_group(int q) const {
-        const int grp = q % kGroups;
-        mbar_wait(bar_u32 + 8u * grp, (uint32_t)(q / kGroups) & 1u);
+    __device__ __forceinline__ void wait_group(int q, int grp, uint32_t parity) const {
+        mbar_wait(bar_u32 + 8u * grp, parity);
         if (edge_strip) {
             // clamp-to-self columns (weather_simulation.cpp:510-511): column -1 := column 0, column W := column W-1
             if (lane == 0) {
@@ -383,9 +398,9 @@ struct SweepT {
     }
 
     // After iteration 3q of triple q the rows of triple q-2 are dead: their group takes the rows of triple q+1.
-    __device__ __forceinline__ void refill(int q) const {
+    __device__ __forceinline__ void refill(int q, int grp_next) const {
         __syncwarp();  // every lane has consumed its reads of the dead group
-        if (lane == 0) issue_group(q + 1);
+        if (lane == 0) issue_group(q + 1, grp_next);
     }
 
     __device__ __forceinline__ void run() const {
@@ -396,9 +411,12 @@ struct SweepT {
         G.b = base + 2 * 3 * L::ROW_ELEMS;     // group 2 (triple -1: never read)
         G.c = base + 1 * 3 * L::ROW_ELEMS;     // group 1 (triple -2: never read; next to be filled)
         const int ntriples = (niter + 2) / 3;
+        int grp = 0;          // ring group of triple q (q mod 3) and the parity of its mbarrier (q / 3 mod 2)
+        uint32_t parity = 0;
         for (int q = 0; q < ntriples; ++q) {
             const int n = 3 * q;
-            wait_group(q);
+            const int grp_next = grp == kGroups - 1 ? 0 : grp + 1;
+            wait_group(q, grp, parity);
             // steady state: pipeline full, no domain edge within reach of any stage, interior strip
             const int r_last = y0 - NST + n - NST;      // smallest center row touched in this triple
             const int r_first = y0 - NST + (n + 2) - 1; // largest
@@ -406,9 +424,11 @@ struct SweepT {
             // one code body for both cases (it has to fit the instruction cache): in the steady state the
             // boundary tests are skipped by uniform branches
             iteration<0>(Lv, n, G, fast);
-            refill(q);
+            refill(q, grp_next);
             if (fast || n + 1 < niter) iteration<1>(Lv, n + 1, G, fast);
             if (fast || n + 2 < niter) iteration<2>(Lv, n + 2, G, fast);
+            if (grp_next == 0) parity ^= 1u;
+            grp = grp_next;
             const T *t = G.c;  // rotate: triple q+1 lives where triple q-2 lived
             G.c = G.b;
             G.b = G.a;
@@ -470,7 +490,7 @@ __global__ void __launch_bounds__(32, MINB)
         for (int s = 0; s < kGroups; ++s) mbar_init(sw.bar_u32 + 8u * s, 1);
         fence_mbar_init();
         fence_proxy_async();
-        sw.issue_group(0);
+        sw.issue_group(0, 0);
     }
     __syncwarp();
     sw.run();
