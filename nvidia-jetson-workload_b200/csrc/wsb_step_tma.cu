@@ -79,6 +79,26 @@ struct SmemIO<float, 2> {
     }
 };
 template <>
+struct SmemIO<float, 4> {
+    static __device__ __forceinline__ void ld(const float *p, float (&r)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float *p, const float (&r)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+};
+template <>
+struct SmemIO<double, 2> {
+    static __device__ __forceinline__ void ld(const double *p, double (&r)[2]) {
+        const double2 t = *reinterpret_cast<const double2 *>(p);
+        r[0] = t.x; r[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(double *p, const double (&r)[2]) {
+        *reinterpret_cast<double2 *>(p) = make_double2(r[0], r[1]);
+    }
+};
+template <>
 struct SmemIO<double, 1> {
     static __device__ __forceinline__ void ld(const double *p, double (&r)[1]) { r[0] = *p; }
     static __device__ __forceinline__ void st(double *p, const double (&r)[1]) { *p = r[0]; }
@@ -125,7 +145,7 @@ struct SweepT {
     bool st_vec, st_e[V], ragged;
 
     // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
-    static constexpr bool kPacked = std::is_same<T, float>::value && V == 2 && RECIP;
+    static constexpr bool kPacked = std::is_same<T, float>::value && V % 2 == 0 && RECIP;
 
     __device__ __forceinline__ SweepT(const Geometry<T> &g_, const Physics<T> &ph_, const StepArgs<T> &a_)
         : g(g_), ph(ph_), a(a_) {}
@@ -212,7 +232,9 @@ struct SweepT {
             const T from_left = __shfl_up_sync(kFull, r.f[f][V - 1], 1);
             if (c0 + V - 1 == -1) r.f[f][V - 1] = from_right;           // column -1 := column 0
             if (c0 == g.W) r.f[f][0] = from_left;                       // column W := column W-1
-            if (V == 2 && c0 + 1 == g.W) r.f[f][V - 1] = r.f[f][0];
+#pragma unroll
+            for (int e = 1; e < V; ++e)
+                if (c0 + e == g.W) r.f[f][e] = r.f[f][e - 1];           // ... when W-1 and W share a lane
         }
     }
 
@@ -225,14 +247,23 @@ struct SweepT {
             Rgt[f] = __shfl_down_sync(kFull, C.f[f][0], 1);
         }
         if constexpr (kPacked) {
-            auto P = [](const T(&r)[V]) { return F2{(float)r[0], (float)r[1]}; };
-            F2 du, dv, dh;
-            tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]), (float)Lft[0], (float)Rgt[0], P(U.f[0]), P(D.f[0]),
-                          (float)Lft[1], (float)Rgt[1], P(U.f[1]), P(D.f[1]), (float)Lft[2], (float)Rgt[2], P(U.f[2]),
-                          P(D.f[2]), du, dv, dh);
-            k.f[0][0] = du.x; k.f[0][1] = du.y;
-            k.f[1][0] = dv.x; k.f[1][1] = dv.y;
-            k.f[2][0] = dh.x; k.f[2][1] = dh.y;
+            // pairs of adjacent cells (2p, 2p+1): outer neighbours come from the lane's other cells or the shuffles
+#pragma unroll
+            for (int p = 0; p < V / 2; ++p) {
+                auto P = [p](const T(&r)[V]) { return F2{(float)r[2 * p], (float)r[2 * p + 1]}; };
+                float lf[3], rg[3];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    lf[f] = (p == 0) ? (float)Lft[f] : (float)C.f[f][2 * p - 1];
+                    rg[f] = (p == V / 2 - 1) ? (float)Rgt[f] : (float)C.f[f][2 * p + 2];
+                }
+                F2 du, dv, dh;
+                tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1], rg[1],
+                              P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
+                k.f[0][2 * p] = du.x; k.f[0][2 * p + 1] = du.y;
+                k.f[1][2 * p] = dv.x; k.f[1][2 * p + 1] = dv.y;
+                k.f[2][2 * p] = dh.x; k.f[2][2 * p + 1] = dh.y;
+            }
             return;
         }
 #pragma unroll
@@ -300,11 +331,13 @@ struct SweepT {
             if constexpr (kPacked) {
                 const F2 c2 = f2_splat((float)c);
 #pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    const F2 rr = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, c2,
-                                            F2{(float)k.f[f][0], (float)k.f[f][1]});
-                    t.f[f][0] = rr.x; t.f[f][1] = rr.y;
-                }
+                for (int f = 0; f < 3; ++f)
+#pragma unroll
+                    for (int p = 0; p < V; p += 2) {
+                        const F2 rr = axpy_pair(F2{(float)yb.f[f][p], (float)yb.f[f][p + 1]}, c2,
+                                                F2{(float)k.f[f][p], (float)k.f[f][p + 1]});
+                        t.f[f][p] = rr.x; t.f[f][p + 1] = rr.y;
+                    }
             } else {
 #pragma unroll
                 for (int f = 0; f < 3; ++f)
@@ -354,13 +387,15 @@ struct SweepT {
                 if constexpr (kPacked) {
                     const F2 dt6 = f2_splat((float)a.dt6);
 #pragma unroll
-                    for (int f = 0; f < 3; ++f) {
-                        const F2 k4 = F2{(float)k.f[f][0], (float)k.f[f][1]};
-                        const F2 rr = rk4_combine_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt6, k4,
-                                                       F2{(float)k2.f[f][0], (float)k2.f[f][1]},
-                                                       F2{(float)k3.f[f][0], (float)k3.f[f][1]}, k4);
-                        o.f[f][0] = rr.x; o.f[f][1] = rr.y;
-                    }
+                    for (int f = 0; f < 3; ++f)
+#pragma unroll
+                        for (int p = 0; p < V; p += 2) {
+                            const F2 k4 = F2{(float)k.f[f][p], (float)k.f[f][p + 1]};
+                            const F2 rr = rk4_combine_pair(F2{(float)yb.f[f][p], (float)yb.f[f][p + 1]}, dt6, k4,
+                                                           F2{(float)k2.f[f][p], (float)k2.f[f][p + 1]},
+                                                           F2{(float)k3.f[f][p], (float)k3.f[f][p + 1]}, k4);
+                            o.f[f][p] = rr.x; o.f[f][p + 1] = rr.y;
+                        }
                 } else {
 #pragma unroll
                     for (int f = 0; f < 3; ++f)
@@ -372,11 +407,13 @@ struct SweepT {
             } else if constexpr (kPacked) {
                 const F2 dt2 = f2_splat((float)a.dt);
 #pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    const F2 rr = axpy_pair(F2{(float)yb.f[f][0], (float)yb.f[f][1]}, dt2,
-                                            F2{(float)k.f[f][0], (float)k.f[f][1]});
-                    o.f[f][0] = rr.x; o.f[f][1] = rr.y;
-                }
+                for (int f = 0; f < 3; ++f)
+#pragma unroll
+                    for (int p = 0; p < V; p += 2) {
+                        const F2 rr = axpy_pair(F2{(float)yb.f[f][p], (float)yb.f[f][p + 1]}, dt2,
+                                                F2{(float)k.f[f][p], (float)k.f[f][p + 1]});
+                        o.f[f][p] = rr.x; o.f[f][p + 1] = rr.y;
+                    }
             } else {
 #pragma unroll
                 for (int f = 0; f < 3; ++f)
@@ -540,8 +577,13 @@ template <>
 cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float> &ph, const StepArgs<float> &a,
                                    int nstages, cudaStream_t st) {
     switch (nstages) {
-        case 1: return launch_impl<float, 1, 2, 20>(g, ph, a, st);
-        case 2: return launch_impl<float, 2, 2, 16>(g, ph, a, st);
+        // cells per lane (strip = 32 x cells columns), measured on B200 (profiles/r1/README.md): Euler is best at 2
+        // (0.271 vs 0.276 ms at 8192^2), RK2 at 4 (1.79 vs 1.91 ms at 2048^2 x 64); WSB_CELLS_PER_LANE overrides for A/B
+        case 1: return env_int("WSB_CELLS_PER_LANE", 2) == 4 ? launch_impl<float, 1, 4, 16>(g, ph, a, st)
+                                                              : launch_impl<float, 1, 2, 20>(g, ph, a, st);
+        case 2: return env_int("WSB_CELLS_PER_LANE", 4) == 2 ? launch_impl<float, 2, 2, 16>(g, ph, a, st)
+                                                              : launch_impl<float, 2, 4, 12>(g, ph, a, st);
+        // RK4 at 4 cells per lane: 168 registers, 9 warps per SM, 0.77 ms vs 0.623 ms -> not instantiated
         case 4: return launch_impl<float, 4, 2, 18>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
@@ -551,8 +593,11 @@ template <>
 cudaError_t launch_step_tma<double>(const Geometry<double> &g, const Physics<double> &ph, const StepArgs<double> &a,
                                     int nstages, cudaStream_t st) {
     switch (nstages) {
-        case 1: return launch_impl<double, 1, 1, 20>(g, ph, a, st);
-        case 2: return launch_impl<double, 2, 1, 16>(g, ph, a, st);
+        // two cells per lane: Barotropic 16384^2 Euler 2.11 ms (0.93 of HBM peak) vs 2.54 ms with one
+        case 1: return env_int("WSB_CELLS_PER_LANE", 2) == 1 ? launch_impl<double, 1, 1, 20>(g, ph, a, st)
+                                                              : launch_impl<double, 1, 2, 16>(g, ph, a, st);
+        case 2: return env_int("WSB_CELLS_PER_LANE", 2) == 1 ? launch_impl<double, 2, 1, 16>(g, ph, a, st)
+                                                              : launch_impl<double, 2, 2, 12>(g, ph, a, st);
         case 4: return launch_impl<double, 4, 1, 12>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
