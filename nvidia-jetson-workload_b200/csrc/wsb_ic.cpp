@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "wsb_internal.h"
@@ -252,6 +254,41 @@ int ic_dispatch(const char *name, const Params &a, std::mt19937 &rng, const char
     return -1;
 }
 
+// Rows [g.ys, g.ye) split over host threads. Every cell is a pure function of (x, y) -- and, for "random", of the
+// generator position, which each thread reaches with discard() -- so the result does not depend on the split.
+int ic_dispatch_parallel(const char *name, const Params &a, std::mt19937 &rng, const char *profile,
+                         const HostFields &g) {
+    const int rows = g.ye - g.ys;
+    const long long cells = (long long)rows * g.W;
+    int nthreads = (int)std::min<long long>(std::max(1u, std::min(32u, std::thread::hardware_concurrency())),
+                                            cells / (1 << 16));
+    if (const char *e = std::getenv("WSB_IC_THREADS")) nthreads = std::atoi(e);
+    nthreads = std::max(1, std::min(nthreads, rows));
+    const bool is_random = name && std::strcmp(name, "random") == 0;
+    int mask = 0;
+    if (nthreads == 1) {
+        mask = ic_dispatch(name, a, rng, profile, g);
+        return mask;
+    }
+    std::vector<int> masks(nthreads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const int y0 = g.ys + (int)((long long)rows * t / nthreads), y1 = g.ys + (int)((long long)rows * (t + 1) / nthreads);
+        pool.emplace_back([&, t, y0, y1] {
+            const size_t off = (size_t)(y0 - g.ys) * g.W;
+            auto at = [off](float *f) { return f ? f + off : f; };
+            const HostFields sub{g.W, g.H, y0, y1, at(g.u), at(g.v), at(g.h), at(g.p), at(g.t), at(g.q)};
+            std::mt19937 local = rng;
+            if (is_random) local.discard(3ULL * off);
+            masks[t] = ic_dispatch(name, a, local, profile, sub);
+        });
+    }
+    for (auto &th : pool) th.join();
+    if (is_random) rng.discard(3ULL * (unsigned long long)cells);
+    for (int m : masks) mask = (m < 0 || mask < 0) ? -1 : (mask | m);
+    return mask;
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,7 +303,7 @@ int wsb_ic_fill_host(const char *name, const double *params, int32_t nparams, ui
     const Params a{params, nparams};
     const HostFields g{width, height, 0, height, u, v, h, p, t, q};
     std::mt19937 rng(static_cast<int>(seed));
-    if (ic_dispatch(name, a, rng, profile, g) < 0)
+    if (ic_dispatch_parallel(name, a, rng, profile, g) < 0)
         return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
     return WSB_OK;
 }
@@ -294,7 +331,7 @@ int wsb_ic_apply(wsb_grid *grid, const char *name, const double *params, int32_t
         const int ye = std::min(gi.height, ys + block);
         const HostFields g{gi.width, Hglobal, row0 + ys, row0 + ye, buf[0].data(), buf[1].data(), buf[2].data(),
                            buf[3].data(), buf[4].data(), buf[5].data()};
-        const int mask = ic_dispatch(name, a, rng, profile, g);
+        const int mask = ic_dispatch_parallel(name, a, rng, profile, g);
         if (mask < 0)
             return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
         for (int k = 0; k < 6; ++k)

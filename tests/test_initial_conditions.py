@@ -116,3 +116,18 @@ def test_unknown_ic_is_an_error():
     buf = np.zeros((4, 4), np.float32)
     st = lib.wsb_ic_fill_host(b"bogus", None, 0, 0, None, 4, 4, 1.0, 1.0, buf.ctypes.data, None, None, None, None, None)
     assert st == _capi.WSB_ERR_INVALID_ARGUMENT and "bogus" in _capi.last_error()
+
+
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_threaded_fill_is_split_independent(threads, monkeypatch):
+    """Rows are evaluated on several host threads (wsb_ic.cpp: ic_dispatch_parallel); every split must give the
+    bytes of the serial evaluation, including the mt19937 stream of "random"."""
+    W, H = 97, 61
+    names = [c[0] for c in CASES] + ["random", "standard_atmosphere", "tropical_atmosphere"]
+    monkeypatch.setenv("WSB_IC_THREADS", "1")
+    serial = {n: ours(n, (), W, H, seed=7) for n in names}
+    monkeypatch.setenv("WSB_IC_THREADS", str(threads))
+    for n in names:
+        got = ours(n, (), W, H, seed=7)
+        for k in "uvhptq":
+            assert got[k].tobytes() == serial[n][k].tobytes(), (n, k)
