@@ -208,7 +208,7 @@ struct wsb_sim {
     void *k3[3] = {nullptr, nullptr, nullptr};
     bool diag_dirty = false;  // vorticity/divergence need recomputing from the current u, v
     bool halo_valid = false;  // ghost rows of the current state are up to date (nranks > 1)
-    static constexpr int kMaxSlabs = 32;  // row slabs of the streamed host step
+    static constexpr int kMaxSlabs = 128;  // row slabs of the streamed host step
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_up[kMaxSlabs] = {}, ev_done[kMaxSlabs] = {};
     cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
@@ -1029,12 +1029,27 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
     a.dt = (T)s->dt;
     a.half_dt = T(0.5f) * a.dt;
     a.dt6 = a.dt / T(6.0f);
-    const int nslabs = std::max(1, std::min((int)wsb_sim::kMaxSlabs, H / 256));
+    // 16 slabs: the call ends one slab after the last upload ((1 + 1/n) x the transfer) and every slab costs about
+    // 50-100 us of event / launch latency in the upload -> step -> download chain (profiles/r1/e2e_sweep*.txt)
+    int want_slabs = 16;
+    if (const char *e = std::getenv("WSB_HOST_SLABS")) want_slabs = std::atoi(e);
+    // short row chunks: a slab's launch sits between its upload and its download, so its LATENCY counts, not its
+    // efficiency (the whole step is 0.6 ms of an 18 ms transfer)
+    a.rows_per_chunk = 16;
+    if (const char *e = std::getenv("WSB_HOST_RPC")) a.rows_per_chunk = std::atoi(e);
+    const int nslabs = std::max(1, std::min(std::min((int)wsb_sim::kMaxSlabs, want_slabs), H / 64));
+    // WSB_HOST_TRACE=1: device timeline of the three streams of one call (tuning aid, prints to stderr)
+    const bool trace = std::getenv("WSB_HOST_TRACE") != nullptr;
+    cudaEvent_t tr[4] = {};
+    if (trace) {
+        for (auto &e : tr) WSB_CUDA(cudaEventCreate(&e));
+    }
     const int rows_per_slab = (H + nslabs - 1) / nslabs;
     // everything already enqueued on the main stream (previous steps) precedes the first upload
     WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));
     WSB_CUDA(cudaStreamWaitEvent(s->h2d_stream, s->ev_edge, 0));
     WSB_CUDA(cudaStreamWaitEvent(s->d2h_stream, s->ev_edge, 0));
+    if (trace) WSB_CUDA(cudaEventRecord(tr[0], s->h2d_stream));
     int done_rows = 0;
     for (int i = 0; i < nslabs; ++i) {
         const int r0 = i * rows_per_slab, r1 = std::min(H, r0 + rows_per_slab);
@@ -1056,6 +1071,7 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
         s->metrics.kernel_launches += 1;
         WSB_CUDA(cudaEventRecord(s->ev_done[i], s->stream));
         WSB_CUDA(cudaStreamWaitEvent(s->d2h_stream, s->ev_done[i], 0));
+        if (trace && done_rows == 0) WSB_CUDA(cudaEventRecord(tr[2], s->d2h_stream));
         for (int l = 0; l < g->L; ++l)
             for (int k = 0; k < 3; ++k) {
                 const char *src = (const char *)plane_origin(s, s->next[k]) +
@@ -1065,6 +1081,18 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
                                            cudaMemcpyDeviceToHost, s->d2h_stream));
             }
         done_rows = end;
+    }
+    if (trace) {
+        WSB_CUDA(cudaEventRecord(tr[1], s->h2d_stream));
+        WSB_CUDA(cudaEventRecord(tr[3], s->d2h_stream));
+        WSB_CUDA(cudaEventSynchronize(tr[3]));
+        WSB_CUDA(cudaEventSynchronize(tr[1]));
+        float up = 0, d0 = 0, d1 = 0;
+        cudaEventElapsedTime(&up, tr[0], tr[1]);
+        cudaEventElapsedTime(&d0, tr[0], tr[2]);
+        cudaEventElapsedTime(&d1, tr[0], tr[3]);
+        std::fprintf(stderr, "[wsb] step_host: %d slabs; uploads 0..%.3f ms, downloads %.3f..%.3f ms\n", nslabs, up, d0, d1);
+        for (auto &e : tr) cudaEventDestroy(e);
     }
     // the main stream rejoins the copy streams: later work sees a complete state
     WSB_CUDA(cudaEventRecord(s->ev_halo, s->d2h_stream));
