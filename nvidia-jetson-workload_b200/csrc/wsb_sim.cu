@@ -1050,6 +1050,22 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
     WSB_CUDA(cudaStreamWaitEvent(s->h2d_stream, s->ev_edge, 0));
     WSB_CUDA(cudaStreamWaitEvent(s->d2h_stream, s->ev_edge, 0));
     if (trace) WSB_CUDA(cudaEventRecord(tr[0], s->h2d_stream));
+    if (s->comm) {
+        // row slabs: the neighbours need this rank's first and last `halo` input rows before their edge rows can
+        // step, so those go up first and are exchanged (NCCL, comm stream) while the slabs stream behind them
+        const int bands[2][2] = {{0, halo}, {H - halo, H}};
+        for (const auto &b : bands)
+            for (int l = 0; l < g->L; ++l)
+                for (int k = 0; k < 3; ++k) {
+                    char *dst = (char *)g->origin(k) + ((size_t)l * g->level_stride + (size_t)b[0] * g->pitch) * es;
+                    const char *src = (const char *)in[k] + ((size_t)l * H + b[0]) * row_bytes;
+                    WSB_CUDA(copy_rows(dst, pitch_bytes, src, row_bytes, row_bytes, (size_t)(b[1] - b[0]),
+                                       cudaMemcpyHostToDevice, s->h2d_stream));
+                }
+        WSB_CUDA(cudaEventRecord(s->ev_interior, s->h2d_stream));
+        WSB_TRY(sim_exchange(s, cur3, halo, s->ev_interior));
+        WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));  // ghost rows precede the first launch
+    }
     int done_rows = 0;
     for (int i = 0; i < nslabs; ++i) {
         const int r0 = i * rows_per_slab, r1 = std::min(H, r0 + rows_per_slab);
@@ -1107,7 +1123,8 @@ int wsb_sim_step_host(wsb_sim *s, const void *u, const void *v, const void *h, v
     if (!s || !u || !v || !h || !out_u || !out_v || !out_h) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
     WSB_CUDA(cudaSetDevice(s->cur.device));
     wsb_grid *g = &s->cur;
-    const bool pipelined = is_step_path(s->path) && !s->comm && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
+    const bool pipelined = is_step_path(s->path) && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS &&
+                           (!s->comm || g->H >= 2 * s->nstages);
     if (!pipelined) {  // same result, unpipelined: upload, step, download
         const void *in[3] = {u, v, h};
         void *out[3] = {out_u, out_v, out_h};
@@ -1117,6 +1134,10 @@ int wsb_sim_step_host(wsb_sim *s, const void *u, const void *v, const void *h, v
         return WSB_OK;
     }
     const auto t0 = std::chrono::steady_clock::now();
+    if (s->comm) {  // asynchronous earlier steps may still be exchanging ghost rows
+        WSB_CUDA(cudaStreamSynchronize(s->edge_stream));
+        WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
+    }
     WSB_TRY(sim_begin_timing(s));
     const void *in[3] = {u, v, h};
     void *out[3] = {out_u, out_v, out_h};
@@ -1126,6 +1147,7 @@ int wsb_sim_step_host(wsb_sim *s, const void *u, const void *v, const void *h, v
     for (int k = 0; k < 3; ++k) std::swap(g->f[k].base, s->next[k]);
     for (int k = WSB_FIELD_PRESSURE; k <= WSB_FIELD_HUMIDITY; ++k) std::swap(g->f[k], s->alt[k]);
     s->diag_dirty = true;
+    s->halo_valid = false;  // the new state's ghost rows have not been exchanged
     if (s->dtype == WSB_F32) s->time = (double)((float)s->time + (float)s->dt);
     else s->time += s->dt;
     s->step += 1;

@@ -56,6 +56,34 @@ def _worker(rank, world, port, cases, out_q):
                         msgs.append(f"{W}x{H} integ{integ} {kernel} {dtype} field {k}: differs "
                                     f"({int((a != b).sum())} cells)")
                 o.close()
+        # streamed host step on slabs: edge rows go up first and are exchanged while the slabs stream behind them;
+        # a device-resident step after it must find the state (and re-exchange the ghost rows)
+        for (W, H, integ, dtype) in ((200, 16 * world + 5, 2, "float32"), (1100, 1300, 2, "float32"), (530, 700, 0, "float64")):
+            dt = np.dtype(dtype)
+            u, v, h = syn.white_noise_state(W, H, dtype=dt, seed=W + H)
+            sim = wd.slab_simulation(W, H, rank, world, device_id=rank, integrator=integ, kernel="step_fused_tma",
+                                     coriolis_f=0.1, max_time=1e30, dtype=dt)
+            r0, n = sim.local_rows
+            ins = [a[r0:r0 + n].copy() for a in (u, v, h)]  # copies: the second call writes into them
+            outs = [np.empty((n, W), dt) for _ in range(3)]
+            sim.step_host(*ins, *outs)
+            sim.step_host(*outs, *ins)      # second step fed from the first one's host output
+            sim.step(1)                     # third, device resident
+            got = {k: wd.gather_rows(sim.get_field(k), 0) for k in ("u", "v", "h")}
+            two = {k: wd.gather_rows(a, 0) for k, a in zip(("u", "v", "h"), ins)}
+            sim.close()
+            if rank == 0:
+                o = Oracle(W, H, 0, integ, coriolis_f=0.1, dtype=dt)
+                o.set_state(u, v, h)
+                o.step(2)
+                for k in two:
+                    if two[k].tobytes() != o.get_field(k).tobytes():
+                        msgs.append(f"step_host x2 {W}x{H} integ{integ} {dtype} field {k} differs")
+                o.step(1)
+                for k in got:
+                    if got[k].tobytes() != o.get_field(k).tobytes():
+                        msgs.append(f"step_host x2 + step {W}x{H} integ{integ} {dtype} field {k} differs")
+                o.close()
         # initial conditions on slabs: each rank evaluates ITS rows of the global field (incl. the sequential RNG)
         import ctypes
         W, H = 96, 61
