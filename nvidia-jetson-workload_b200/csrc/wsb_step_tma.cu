@@ -3,21 +3,25 @@
 //
 //   * each warp owns a strip of 32*V columns and sweeps down the rows with the same time skew as the
 //     register variant (stage s works on row n-s when row n of y arrives);
-//   * y rows land in a per-warp shared-memory ring (3 groups of 3 rows) through cp.async.bulk (global ->
-//     shared, SASS UBLKCP), one mbarrier per group; lane 0 is the producer: as soon as the rows of triple
-//     q-2 are dead it re-arms their group with the rows of triple q+1, so HBM latency is hidden without
-//     spending registers on prefetch;
+//   * y rows land in a per-warp shared-memory ring (3 groups of 3 rows) through the TMA engine, one mbarrier
+//     per group: in the common case ONE tiled copy per field (cp.async.bulk.tensor.3d over a CUtensorMap of
+//     the plane, box = strip width x 3 rows, SASS UTMALDG; out-of-range columns are zero-filled by the
+//     hardware), at the clamped domain top/bottom row-wise 1-D bulk copies (SASS UBLKCP). One elected lane is
+//     the producer: as soon as the rows of triple q-2 are dead it re-arms their group with the rows of
+//     triple q+1, so HBM latency is hidden without spending registers on prefetch;
 //   * y is re-read from the ring wherever a stage needs it (stencil rows of stage 1, base rows y + c*k),
 //     the k2/k3 rows the RK4 combine needs later are parked in shared memory too (private per lane, no
 //     synchronisation), and only the 3-row windows of the intermediate stage states stay in registers:
-//     ~110 registers instead of ~170, i.e. 16 instead of 12 resident warps per SM, and a 3x instead of 6x
-//     unrolled loop body that fits the instruction cache;
+//     92 registers instead of ~170, i.e. 18 instead of 12 resident warps per SM (shared-memory limited), and
+//     a 3x instead of 6x unrolled loop body;
 //   * a steady-state fast path (interior strip, pipeline full, no domain edge in reach) runs without a
 //     single boundary test; the general path is the register variant's logic.
 //
 // Arithmetic per cell is wsb_arith.cuh: bit-identical to every other path and to the CPU oracle.
 #include "wsb_arith.cuh"
 #include "wsb_internal.h"
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstdint>
 #include <cstdlib>
@@ -57,6 +61,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// TMA tiled copy: a box of the 3-D tensor (x, row, level) -> shared memory; out-of-range elements arrive as zeros
+// and count towards complete_tx like the others (SASS: UTMALDG)
+__device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -113,6 +125,10 @@ struct Layout {
     static constexpr int FIELD_BYTES = SW * (int)sizeof(T);
     static constexpr int ROW_ELEMS = 3 * SW;
     static constexpr int ROW_BYTES = 3 * FIELD_BYTES;
+    // a ring group holds 3 rows as [field][row][SW]: one TMA box (SW columns x 3 rows) per field
+    static constexpr int GROUP_ELEMS = 3 * ROW_ELEMS;
+    static constexpr int GROUP_BYTES = 3 * ROW_BYTES;
+    static __host__ __device__ constexpr int y_elem(int row_in_group, int field) { return (field * 3 + row_in_group) * SW; }
     // RK4 parks two 3-row rings in shared memory (k2 and k3; classical opt-in: k1, k1+2k2, k1+2k2+2k3)
     static __host__ __device__ constexpr int k_rows(bool classical) { return NST == 4 ? (classical ? 9 : 6) : 0; }
     static __host__ __device__ constexpr int smem_bytes(bool classical) { return (kRing + k_rows(classical)) * ROW_BYTES + kGroups * 8; }
@@ -140,6 +156,7 @@ struct SweepT {
     const Physics<T> &ph;
     const StepArgs<T> &a;
     PhysicsF2 ph2;  // splatted constants of the packed path
+    const CUtensorMap *tm_u, *tm_v, *tm_h;  // tiled-TMA descriptors of the y_n planes (kernel parameters)
     int lane, c0, xs;
     bool edge_strip, fix_left, fix_right;
     int y0, niter, gmin, gmax, out_lo, out_hi;
@@ -159,8 +176,7 @@ struct SweepT {
         : g(g_), ph(ph_), a(a_) {}
 
     // ---- producer side (lane 0): one group = 3 consecutive rows, one mbarrier -------------------------
-    // src_off: element offset of row (y0 - NST + 3q), column xs in the planes (what run() carries along)
-    __device__ __forceinline__ void issue_group(int q, int grp, long long src_off) const {
+    __device__ __forceinline__ void issue_group(int q, int grp) const {
         const int m0 = 3 * q;
         const int nr = min(3, niter - m0);
         if (nr <= 0) return;
@@ -168,19 +184,13 @@ struct SweepT {
         mbar_expect_tx(bar, (uint32_t)nr * L::ROW_BYTES);
         const int r0 = y0 - NST + m0;
         if (nr == 3 && r0 >= gmin && r0 + 2 < gmax) {
-            // common case: three consecutive in-domain rows -- one base address per field, then a stride
-            const long long off = src_off;
-            const size_t pitch_bytes = (size_t)g.pitch * sizeof(T);
-            const char *pu = reinterpret_cast<const char *>(a.Y.u + off);
-            const char *pv = reinterpret_cast<const char *>(a.Y.v + off);
-            const char *ph_ = reinterpret_cast<const char *>(a.Y.h + off);
-            const uint32_t dst = ring_u32 + (uint32_t)(grp * 3) * L::ROW_BYTES;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                bulk_g2s(dst + i * L::ROW_BYTES, pu + i * pitch_bytes, L::FIELD_BYTES, bar);
-                bulk_g2s(dst + i * L::ROW_BYTES + L::FIELD_BYTES, pv + i * pitch_bytes, L::FIELD_BYTES, bar);
-                bulk_g2s(dst + i * L::ROW_BYTES + 2 * L::FIELD_BYTES, ph_ + i * pitch_bytes, L::FIELD_BYTES, bar);
-            }
+            // common case, three consecutive rows of the slab: one tiled-TMA box (SW columns x 3 rows) per field.
+            // Columns outside [0, W) arrive as zeros (never used: clamp columns are patched in wait_group).
+            const uint32_t dst = ring_u32 + (uint32_t)grp * L::GROUP_BYTES;
+            const int ty = r0 + kLeadRows, tz = (int)blockIdx.z;  // rows count from the start of the allocation
+            tensor_g2s(dst, tm_u, xs, ty, tz, bar);
+            tensor_g2s(dst + 3 * L::FIELD_BYTES, tm_v, xs, ty, tz, bar);
+            tensor_g2s(dst + 6 * L::FIELD_BYTES, tm_h, xs, ty, tz, bar);
             return;
         }
         for (int i = 0; i < nr; ++i) {
@@ -188,10 +198,10 @@ struct SweepT {
             r = max(r, gmin);
             r = min(r, gmax - 1);  // clamp-to-self rows of the reference (weather_simulation.cpp:512-513)
             const long long off = lvl_off + (long long)r * g.pitch + xs;
-            const uint32_t dst = ring_u32 + (uint32_t)(grp * 3 + i) * L::ROW_BYTES;
-            bulk_g2s(dst, a.Y.u + off, L::FIELD_BYTES, bar);
-            bulk_g2s(dst + L::FIELD_BYTES, a.Y.v + off, L::FIELD_BYTES, bar);
-            bulk_g2s(dst + 2 * L::FIELD_BYTES, a.Y.h + off, L::FIELD_BYTES, bar);
+            const uint32_t dst = ring_u32 + (uint32_t)grp * L::GROUP_BYTES;
+            bulk_g2s(dst + L::y_elem(i, 0) * sizeof(T), a.Y.u + off, L::FIELD_BYTES, bar);
+            bulk_g2s(dst + L::y_elem(i, 1) * sizeof(T), a.Y.v + off, L::FIELD_BYTES, bar);
+            bulk_g2s(dst + L::y_elem(i, 2) * sizeof(T), a.Y.h + off, L::FIELD_BYTES, bar);
         }
     }
 
@@ -203,11 +213,11 @@ struct SweepT {
             if (lane == 0) {
                 const int nr = min(3, niter - 3 * q);
                 for (int i = 0; i < nr; ++i) {
-                    T *row = ring + (grp * 3 + i) * L::ROW_ELEMS;
 #pragma unroll
                     for (int f = 0; f < 3; ++f) {
-                        if (fix_left) row[f * L::SW + L::HX - 1] = row[f * L::SW + L::HX];
-                        if (fix_right) row[f * L::SW + (g.W - xs)] = row[f * L::SW + (g.W - xs) - 1];
+                        T *row = ring + grp * L::GROUP_ELEMS + L::y_elem(i, f);
+                        if (fix_left) row[L::HX - 1] = row[L::HX];
+                        if (fix_right) row[g.W - xs] = row[g.W - xs - 1];
                     }
                 }
             }
@@ -219,9 +229,10 @@ struct SweepT {
     template <int PH, int J>
     __device__ __forceinline__ void ld_y(Row<T, V> &dst, const Groups &G) const {
         constexpr int i = PH - J;
-        const T *row = (i >= 0) ? G.a + i * L::ROW_ELEMS : (i >= -3) ? G.b + (3 + i) * L::ROW_ELEMS : G.c + (6 + i) * L::ROW_ELEMS;
+        const T *grp = (i >= 0) ? G.a : (i >= -3) ? G.b : G.c;
+        constexpr int ri = (i >= 0) ? i : (i >= -3) ? 3 + i : 6 + i;
 #pragma unroll
-        for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(row + f * L::SW, dst.f[f]);
+        for (int f = 0; f < 3; ++f) SmemIO<T, V>::ld(grp + L::y_elem(ri, f), dst.f[f]);
     }
     __device__ __forceinline__ void ld_k(Row<T, V> &dst, const T *base, int slot) const {
         const T *row = base + slot * L::ROW_ELEMS;
@@ -444,9 +455,9 @@ struct SweepT {
     }
 
     // After iteration 3q of triple q the rows of triple q-2 are dead: their group takes the rows of triple q+1.
-    __device__ __forceinline__ void refill(int q, int grp_next, long long src_off) const {
+    __device__ __forceinline__ void refill(int q, int grp_next) const {
         __syncwarp();  // every lane has consumed its reads of the dead group
-        if (elect_one()) issue_group(q + 1, grp_next, src_off);  // elect.sync: no divergence bookkeeping around the UBLKCPs
+        if (elect_one()) issue_group(q + 1, grp_next);  // elect.sync: no divergence bookkeeping around the UBLKCPs
     }
 
     __device__ __forceinline__ void run() const {
@@ -462,8 +473,6 @@ struct SweepT {
         // output row of iteration n is y0 - 2*NST + n: the lane's three store addresses advance one row per iteration
         const long long o0 = lvl_off + (long long)(y0 - 2 * NST) * g.pitch + c0;
         T *po[3] = {a.O.u + o0, a.O.v + o0, a.O.h + o0};
-        // rows of triple q + 1 start at row y0 - NST + 3 (q + 1)
-        long long src_off = lvl_off + (long long)(y0 - NST + 3) * g.pitch + xs;
         // steady state (pipeline full, no domain edge within reach of any stage, interior strip) for n in [n_lo, n_hi):
         //   n >= 2*NST, n + 2 < niter, y0 - 2*NST + n > gmin, y0 - NST + n + 1 < gmax
         const int n_lo = max(2 * NST, gmin - y0 + 2 * NST + 1);
@@ -477,8 +486,7 @@ struct SweepT {
             // one code body for both cases (it has to fit the instruction cache): in the steady state the
             // boundary tests are skipped by uniform branches
             iteration<0>(Lv, n, G, fast, po);
-            refill(q, grp_next, src_off);
-            src_off += 3LL * g.pitch;
+            refill(q, grp_next);
             if (fast || n + 1 < niter) iteration<1>(Lv, n + 1, G, fast, po);
             else { po[0] += g.pitch; po[1] += g.pitch; po[2] += g.pitch; }
             if (fast || n + 2 < niter) iteration<2>(Lv, n + 2, G, fast, po);
@@ -494,7 +502,9 @@ struct SweepT {
 
 template <typename T, int NST, int V, bool RECIP, int MINB, bool CL>
 __global__ void __launch_bounds__(32, MINB)
-    step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk) {
+    step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk,
+                    const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+                    const __grid_constant__ CUtensorMap tm_h) {
     using L = Layout<T, NST, V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
@@ -512,6 +522,9 @@ __global__ void __launch_bounds__(32, MINB)
     sw.ph2.rdy = f2_splat((float)ph.rdy);
     sw.ph2.g = f2_splat((float)ph.g);
     sw.ph2.f = f2_splat((float)ph.f);
+    sw.tm_u = &tm_u;
+    sw.tm_v = &tm_v;
+    sw.tm_h = &tm_h;
     sw.lane = lane;
     sw.xs = strip * L::OUTW - L::HX;
     sw.c0 = sw.xs + lane * V;
@@ -545,7 +558,7 @@ __global__ void __launch_bounds__(32, MINB)
         for (int s = 0; s < kGroups; ++s) mbar_init(sw.bar_u32 + 8u * s, 1);
         fence_mbar_init();
         fence_proxy_async();
-        sw.issue_group(0, 0, sw.lvl_off + (long long)(y0 - NST) * g.pitch + sw.xs);
+        sw.issue_group(0, 0);
     }
     __syncwarp();
     sw.run();
@@ -563,6 +576,38 @@ int rows_per_chunk_default() {
     return v > 0 ? v : 64;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// One y_n plane as a 3-D tensor (x, row incl. the lead rows, level); box = one strip width x 3 rows.
+template <typename T>
+cudaError_t make_plane_map(CUtensorMap *map, const Geometry<T> &g, const T *origin, int strip_width) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    void *base = const_cast<T *>(origin) - (size_t)kLeadRows * g.pitch;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)(g.H + 2 * kLeadRows), (cuuint64_t)g.L};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(T), (cuuint64_t)g.level_stride * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)strip_width, 3u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <typename T, int NST, int V, int MINB>
 cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
     using L = Layout<T, NST, V>;
@@ -572,15 +617,19 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk : rows_per_chunk_default();
     const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
     const dim3 grid(strips, chunks, g.L);
+    CUtensorMap tu, tv, th;
+    if (cudaError_t e = make_plane_map<T>(&tu, g, a.Y.u, L::SW)) return e;
+    if (cudaError_t e = make_plane_map<T>(&tv, g, a.Y.v, L::SW)) return e;
+    if (cudaError_t e = make_plane_map<T>(&th, g, a.Y.h, L::SW)) return e;
     if constexpr (NST == 4) {
         if (a.classical) {  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
-            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc);
-            else step_tma_kernel<T, NST, V, false, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc);
+            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
+            else step_tma_kernel<T, NST, V, false, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
             return cudaGetLastError();
         }
     }
-    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc);
-    else step_tma_kernel<T, NST, V, false, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc);
+    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
+    else step_tma_kernel<T, NST, V, false, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
     return cudaGetLastError();
 }
 
