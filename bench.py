@@ -334,12 +334,12 @@ def run_b200_arm(args, wl, rank, world, local_rank):
                     "one fused tendency+update pass per RK stage",
         }
         if fused and wl["dtype"] == "f32" and wl["integ"] == "rk4" and wl["model"] == "shallow_water":
-            # what actually bounds this kernel: the fp32 pipe. A strip row costs 334
-            # FMA-pipe cycles (221 instructions, packed ones occupy the pipe twice); strips x chunks x
-            # (64 + 2*4) rows per step over 148 SMs x 4 schedulers at the sampled SM clock.
+            # what actually bounds this kernel: the fp32 pipe. One stage of a strip row costs
+            # 83.5 FMA-pipe cycles (packed instructions occupy the pipe twice); a 64-row chunk evaluates
+            # 70 + 68 + 66 + 64 = 268 stage-rows; strips x chunks over 148 SMs x 4 schedulers at the sampled SM clock.
             strips, chunks = -(-W // 56), -(-nrows // 64)
             mhz = (clk.summary()["sm_mhz"] or 1965.0)
-            floor_ms = strips * chunks * 72 * 334 / (148 * 4 * mhz * 1e3)
+            floor_ms = strips * chunks * 268 * 83.5 / (148 * 4 * mhz * 1e3)
             roofline["fp32_pipe"] = {"floor_ms_per_step": floor_ms, "frac": floor_ms / (dev_ms / args.steps),
                                      "note": "no-FMA fp32 work of the bit-exact arithmetic at 128 lanes/clk/SM"}
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")

@@ -161,7 +161,7 @@ struct SweepT {
     bool edge_strip, fix_left, fix_right;
     int y0, niter, gmin, gmax, out_lo, out_hi;
     long long lvl_off;
-    T *ring;        // [kRing][3][SW]
+    T *ring;        // [kGroups][3 fields][3 rows][SW]
     T *k2s;         // [3][3][SW], lane-offset
     T *k3s;         // [3][3][SW], lane-offset
     T *k1s;         // [3][3][SW], lane-offset (classical RK4 only)
@@ -175,7 +175,7 @@ struct SweepT {
     __device__ __forceinline__ SweepT(const Geometry<T> &g_, const Physics<T> &ph_, const StepArgs<T> &a_)
         : g(g_), ph(ph_), a(a_) {}
 
-    // ---- producer side (lane 0): one group = 3 consecutive rows, one mbarrier -------------------------
+    // ---- producer side (one elected lane): one group = 3 consecutive rows, one mbarrier ----------------
     __device__ __forceinline__ void issue_group(int q, int grp) const {
         const int m0 = 3 * q;
         const int nr = min(3, niter - m0);
@@ -456,6 +456,7 @@ struct SweepT {
 
     // After iteration 3q of triple q the rows of triple q-2 are dead: their group takes the rows of triple q+1.
     __device__ __forceinline__ void refill(int q, int grp_next) const {
+        if (edge_strip) fence_proxy_async();  // lane 0 patched clamp columns in that group with generic stores
         __syncwarp();  // every lane has consumed its reads of the dead group
         if (elect_one()) issue_group(q + 1, grp_next);  // elect.sync: no divergence bookkeeping around the UBLKCPs
     }
