@@ -318,7 +318,8 @@ struct SweepT {
     // PURE: the CTA is nowhere near a domain edge (interior strip, every row it loads is a real row): no boundary
     // handling is compiled in at all, pipeline-fill iterations just compute on garbage that is never stored.
     template <int PH, int S1, bool PURE>
-    __device__ __forceinline__ void stage(Windows &Lv, int n, const Groups &G, const bool FAST_, T *const (&po)[3]) const {
+    __device__ __forceinline__ void stage(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool FAST_,
+                                          T *const (&po)[3]) const {
         const bool FAST = PURE || FAST_;
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
@@ -335,16 +336,26 @@ struct SweepT {
                 return;
             }
         }
+        // boundary-free body: the last three y rows are carried in registers (slot = row mod 3), so stage 1 loads
+        // one row per iteration instead of three and stage 2 finds its base row there
+        constexpr bool kYwin = PURE;
         Row<T, V> k, yb;
         if constexpr (S1 == 1) {
-            Row<T, V> U, D;
-            ld_y<PH, 2>(U, G);
-            ld_y<PH, 1>(yb, G);
-            ld_y<PH, 0>(D, G);
-            tendency_row(U, yb, D, k);
+            if constexpr (kYwin) {
+                ld_y<PH, 0>(Yw[PH], G);
+                yb = Yw[(PH + 2) % 3];
+                tendency_row(Yw[(PH + 1) % 3], yb, Yw[PH], k);
+            } else {
+                Row<T, V> U, D;
+                ld_y<PH, 2>(U, G);
+                ld_y<PH, 1>(yb, G);
+                ld_y<PH, 0>(D, G);
+                tendency_row(U, yb, D, k);
+            }
         } else {
             tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k);
-            ld_y<PH, S1>(yb, G);
+            if constexpr (kYwin && S1 == 2) yb = Yw[(PH + 1) % 3];
+            else ld_y<PH, S1>(yb, G);
         }
         if constexpr (S1 < NST) {
             const T c = (NST == 4 && S1 == 3) ? a.dt : a.half_dt;
@@ -446,12 +457,13 @@ struct SweepT {
     }
 
     template <int PH, bool PURE>
-    __device__ __forceinline__ void iteration(Windows &Lv, int n, const Groups &G, const bool fast, T *(&po)[3]) const {
-        stage<PH, 1, PURE>(Lv, n, G, fast, po);
-        if constexpr (NST >= 2) stage<PH, 2, PURE>(Lv, n, G, fast, po);
+    __device__ __forceinline__ void iteration(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool fast,
+                                              T *(&po)[3]) const {
+        stage<PH, 1, PURE>(Lv, Yw, n, G, fast, po);
+        if constexpr (NST >= 2) stage<PH, 2, PURE>(Lv, Yw, n, G, fast, po);
         if constexpr (NST >= 4) {
-            stage<PH, 3, PURE>(Lv, n, G, fast, po);
-            stage<PH, 4, PURE>(Lv, n, G, fast, po);
+            stage<PH, 3, PURE>(Lv, Yw, n, G, fast, po);
+            stage<PH, 4, PURE>(Lv, Yw, n, G, fast, po);
         }
 #pragma unroll
         for (int f = 0; f < 3; ++f) po[f] += g.pitch;
@@ -467,6 +479,7 @@ struct SweepT {
     template <bool PURE>
     __device__ __forceinline__ void run() const {
         Windows Lv;
+        Row<T, V> Yw[3];  // y rows n, n-1, n-2 of the boundary-free body
         Groups G;
         const T *base = ring + lane * V;
         G.a = base;                            // group 0: rows of triple 0
@@ -490,11 +503,11 @@ struct SweepT {
             const bool fast = PURE || (unsigned)(n - n_lo) < n_span;
             // general body: one code path for steady state and boundaries, the boundary tests are skipped by
             // uniform branches in the steady state
-            iteration<0, PURE>(Lv, n, G, fast, po);
+            iteration<0, PURE>(Lv, Yw, n, G, fast, po);
             refill(q, grp_next);
-            if ((!PURE && fast) || n + 1 < niter) iteration<1, PURE>(Lv, n + 1, G, fast, po);
+            if ((!PURE && fast) || n + 1 < niter) iteration<1, PURE>(Lv, Yw, n + 1, G, fast, po);
             else { po[0] += g.pitch; po[1] += g.pitch; po[2] += g.pitch; }
-            if ((!PURE && fast) || n + 2 < niter) iteration<2, PURE>(Lv, n + 2, G, fast, po);
+            if ((!PURE && fast) || n + 2 < niter) iteration<2, PURE>(Lv, Yw, n + 2, G, fast, po);
             if (grp_next == 0) parity ^= 1u;
             grp = grp_next;
             const T *t = G.c;  // rotate: triple q+1 lives where triple q-2 lived
@@ -665,7 +678,9 @@ cudaError_t launch_step_tma<float>(const Geometry<float> &g, const Physics<float
         case 2: return env_int("WSB_CELLS_PER_LANE", 4) == 2 ? launch_impl<float, 2, 2, 16>(g, ph, a, st)
                                                               : launch_impl<float, 2, 4, 12>(g, ph, a, st);
         // RK4 at 4 cells per lane: 168 registers, 9 warps per SM, 0.77 ms vs 0.623 ms -> not instantiated
-        case 4: return launch_impl<float, 4, 2, 18>(g, ph, a, st);
+        // 16 warps per SM = 128 registers: the boundary-free body carries three y rows in registers (120 used);
+        // at 18 warps (96 registers) that spills (0.70 ms), without the carried rows 18 and 16 are equal
+        case 4: return launch_impl<float, 4, 2, 16>(g, ph, a, st);
         default: return cudaErrorNotSupported;
     }
 }
