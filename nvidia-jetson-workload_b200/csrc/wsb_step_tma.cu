@@ -323,6 +323,11 @@ struct SweepT {
         const bool FAST = PURE || FAST_;
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
+        if constexpr (PURE && S1 > 1) {
+            // pipeline fill: the kernel is fp32-pipe bound, the 20 useless stage-rows per 64-row chunk are worth a
+            // uniform branch per stage (stage 1 always runs: it also loads the y row into the carried window)
+            if (n < 2 * S1) return;
+        }
         if (!FAST) {
             if (n < 2 * S1) return;  // pipeline fill
             if (r < gmin) return;
