@@ -201,7 +201,7 @@ def run_reference_arm(args, wl, rank):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------- our arm --
@@ -262,8 +262,9 @@ def run_b200_arm(args, wl, rank, world, local_rank):
     # ---- device-resident throughput: W warm-up steps, then exactly K steps under CUDA events ----
     sim.step(args.warmup)
     launches0 = sim.metrics.kernel_launches
+    sampler = ClockSampler(local_rank)  # NVML initialisation (milliseconds, differs per rank) stays out of the region
     barrier()
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         sim.advance_async(args.steps)
         sim.synchronize()
     dev_ms = sim.last_run_device_ms
@@ -383,14 +384,30 @@ def run_b200_arm(args, wl, rank, world, local_rank):
                 "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                 "sample": f"reference CPU path, {wl['model']} {n}x{n} fp32 {wl['integ']}, {steps} steps after 2 "
                           f"warm-up ({r['seconds']:.1f} s); its throughput is flat in grid size (BASELINE.md section 2)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     sim.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (the NCCL version banner, the
+    # reference module's "Completed N steps" chatter) is sent to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
