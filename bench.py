@@ -330,7 +330,7 @@ def run_b200_arm(args, wl, rank, world, local_rank):
             "stage_per_pass_equivalent_gbs": wl["bpc_stage"] * cells_rank * args.steps / (dev_ms * 1e-3) / 1e9,
             "note": ("whole-step kernel: every RK stage stays on chip, HBM sees one read of y_n and one write of "
                      "y_n+1 per step (%d B/cell-step instead of %d with one pass per stage); for RK4 fp32 the "
-                     "kernel is bound by fp32 issue, not HBM (no FMA allowed for bit parity) -- DESIGN.md section 4"
+                     "kernel is bound by the fp32 pipe, not HBM (no FMA allowed for bit parity) -- DESIGN.md section 4.4"
                      % (wl["bpc_step"], wl["bpc_stage"])) if fused else
                     "one fused tendency+update pass per RK stage",
         }
