@@ -246,6 +246,35 @@ def test_primitive_levels_vs_2d_oracle(kernel):
         s.close()
 
 
+def test_rk4_boundary_free_body_all_instantiations():
+    """The RK4 whole-step kernel runs a second, boundary-free instantiation of the sweep in CTAs away from every
+    domain edge (wsb_step_tma.cu, run<true>). Sizes with such CTAs for fp32 (56-column strips) and fp64
+    (24-column strips), exact-reciprocal and true-division spacings, and a multi-level grid (the level is the
+    third coordinate of the tiled-TMA descriptor)."""
+    W, H = 200, 210
+    for dtype in (np.float32, np.float64):
+        ic = tuple(a.astype(dtype) for a in syn.random_vorticity(W, H, dtype=np.float64))
+        compare_with_oracle(W, H, 0, 2, "step_fused_tma", 12, ic, dtype=dtype, coriolis_f=0.1)
+        compare_with_oracle(W, H, 0, 2, "step_fused_tma", 12, ic, dtype=dtype, dx=0.9, dy=1.1, coriolis_f=0.1)
+    L = 3
+    u0, v0, h0 = syn.random_vorticity(W, H)
+    us = np.stack([u0 * (1.0 + 0.25 * k) for k in range(L)]).astype(np.float32)
+    vs = np.stack([v0 * (1.0 - 0.125 * k) for k in range(L)]).astype(np.float32)
+    hs = np.stack([h0 + 0.5 * k for k in range(L)]).astype(np.float32)
+    s = cuda_sim(W, H, 0, 2, "step_fused_tma", num_levels=L, coriolis_f=0.1)
+    s.set_state(us, vs, hs)
+    s.step(8)
+    got = {n: s.get_field(n) for n in ("u", "v", "h")}
+    s.close()
+    for k in range(L):
+        o = Oracle(W, H, 0, 2, coriolis_f=0.1)
+        o.set_state(us[k], vs[k], hs[k])
+        o.step(8)
+        for n in got:
+            assert_bit_equal(got[n][k], o.get_field(n), f"level {k} {n}")
+        o.close()
+
+
 # ------------------------------------------------------------------ driver semantics / quirks --
 def test_untouched_fields_alternate_like_the_reference():
     """The reference swaps whole grids every step: p/T/q written into 'current' reappear on even steps."""
