@@ -197,6 +197,32 @@ def test_csv_output_manager(ours, tmp_path):
     np.testing.assert_allclose(tab[:, 4].reshape(16, 24), h, rtol=1e-7)
 
 
+def test_proto_slice_output_manager(ours, tmp_path):
+    """weather.proto slice stream (declared by the reference, never produced): one WeatherSimUpdate per interval."""
+    from weather_sim import proto_stream
+    from weather_sim.output import ProtoSliceOutputManager
+    cfg = ours.OutputConfig()
+    cfg.output_dir = str(tmp_path)
+    cfg.prefix = "slices"
+    c = make_config(ours, "ShallowWater", "RungeKutta4", 24, 16)
+    c.output_interval = 5
+    sim = ours.WeatherSimulation(c)
+    sim.set_initial_condition(ours.JetStreamInitialCondition())
+    om = ProtoSliceOutputManager(cfg, run_id="t", stride=2, total_steps=10)
+    sim.set_output_manager(om)
+    sim.initialize()
+    sim.run(10)
+    msgs = proto_stream.read_frames(open(om.path, "rb").read())
+    assert om.output_count == 2 and len(msgs) == 2
+    # last message: u of every 2nd cell, as doubles, in the fixed 47-byte cell records behind the slice header
+    u, _ = sim.get_current_grid().get_velocity_field()
+    sl = proto_stream.encode_slice(0, u[::2, ::2], u[::2, ::2] * 0, u[::2, ::2] * 0, u[::2, ::2] * 0, u[::2, ::2] * 0)
+    assert len(sl) == 2 + 12 * 8 * 47 + 4
+    raw = msgs[1]
+    cells = np.frombuffer(raw[raw.index(b"\x12\x2d"):][:12 * 8 * 47], proto_stream._CELL_DTYPE)
+    assert np.array_equal(cells["u"].reshape(8, 12), u[::2, ::2].astype(np.float64))
+
+
 def test_zero_copy_device_view():
     """fields can be consumed in place through __cuda_array_interface__ (checked with torch)."""
     import torch
