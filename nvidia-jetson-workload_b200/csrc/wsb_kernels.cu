@@ -53,27 +53,92 @@ __global__ void __launch_bounds__(kBX *kBY)
     }
 }
 
+// Vorticity and divergence (weather_grid.cpp:96-100 and :114-118) as a row sweep: a thread owns 16 bytes of a row
+// (4 floats / 2 doubles), walks down kDiagRows rows with u and v in 3-row register windows (every element is read
+// once per chunk: 16 B/cell fp32 of traffic instead of eight scattered loads), takes horizontal neighbours from
+// its own vector or the warp shuffle network (lane 0 / 31: one scalar load), prefetches one row ahead.
+constexpr int kDiagRows = 32;
+constexpr int kDiagThreads = 128;
+
 template <typename T, bool RECIP>
-__global__ void __launch_bounds__(kBX *kBY)
+__global__ void __launch_bounds__(kDiagThreads)
     diagnostics_kernel(const Geometry<T> g, const Physics<T> ph, const T *__restrict__ u, const T *__restrict__ v,
                        T *__restrict__ vort, T *__restrict__ dvg) {
     using A = Ar<T>;
-    const int x = blockIdx.x * kBX + threadIdx.x;
-    const int y = blockIdx.y * kBY + threadIdx.y;
-    if (x >= g.W || y >= g.H) return;
-    const long long i = (long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x;
-    const int gy = g.row0 + y;
-    const long long iL = (x > 0) ? i - 1 : i;
-    const long long iR = (x < g.W - 1) ? i + 1 : i;
-    const long long iU = (gy > 0) ? i - g.pitch : i;
-    const long long iD = (gy < g.Hglobal - 1) ? i + g.pitch : i;
-    // weather_grid.cpp:96-100 and :114-118
-    const T dv_dx = cdiff<T, RECIP>(v[iR], v[iL], ph.ddx, ph.rdx);
-    const T du_dy = cdiff<T, RECIP>(u[iD], u[iU], ph.ddy, ph.rdy);
-    const T du_dx = cdiff<T, RECIP>(u[iR], u[iL], ph.ddx, ph.rdx);
-    const T dv_dy = cdiff<T, RECIP>(v[iD], v[iU], ph.ddy, ph.rdy);
-    vort[i] = A::sub(dv_dx, du_dy);
-    dvg[i] = A::add(du_dx, dv_dy);
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * kDiagThreads + threadIdx.x) * V;
+    const int xl = min(x0, g.pitch - V);  // trailing lanes stay inside the row (their values are never stored)
+    const int y0 = blockIdx.y * kDiagRows, y1 = min(y0 + kDiagRows, g.H);
+    if ((blockIdx.x * kDiagThreads + (threadIdx.x & ~31)) * V >= g.W) return;  // whole warp past the right edge
+    const long long lvl = (long long)blockIdx.z * g.level_stride;
+    const T *ub = u + lvl, *vb = v + lvl;
+
+    struct Vec {
+        T e[V];
+    };
+    auto load = [&](const T *base, int y) {  // row y of this rank (ghost rows are addressable), 128-bit access
+        alignas(16) Vec r;
+        *reinterpret_cast<int4 *>(r.e) = *reinterpret_cast<const int4 *>(base + (long long)y * g.pitch + xl);
+        return r;
+    };
+    // clamp-to-self at the GLOBAL top and bottom (interior slab edges read the neighbour's ghost row)
+    auto up_row = [&](int y) { return (g.row0 + y > 0) ? y - 1 : y; };
+    auto down_row = [&](int y) { return (g.row0 + y < g.Hglobal - 1) ? y + 1 : y; };
+
+    Vec uU = load(ub, up_row(y0)), vU = load(vb, up_row(y0));
+    Vec uC = load(ub, y0), vC = load(vb, y0);
+    Vec uD = load(ub, down_row(y0)), vD = load(vb, down_row(y0));
+    for (int y = y0; y < y1; ++y) {
+        // prefetch the "down" row of the next iteration
+        const int yn = min(y + 1, y1 - 1);
+        const Vec uN = load(ub, down_row(yn)), vN = load(vb, down_row(yn));
+        // horizontal neighbours across threads
+        T uLn = __shfl_up_sync(kFull, uC.e[V - 1], 1), vLn = __shfl_up_sync(kFull, vC.e[V - 1], 1);
+        T uRn = __shfl_down_sync(kFull, uC.e[0], 1), vRn = __shfl_down_sync(kFull, vC.e[0], 1);
+        const long long row = (long long)y * g.pitch;
+        if (lane == 0 && x0 > 0 && x0 < g.W) {
+            uLn = ub[row + x0 - 1];
+            vLn = vb[row + x0 - 1];
+        }
+        if (lane == 31 && x0 + V < g.W) {
+            uRn = ub[row + x0 + V];
+            vRn = vb[row + x0 + V];
+        }
+        alignas(16) Vec zo, dv;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int x = x0 + e;
+            // weather_grid.cpp:93-94 / 111-112: l = max(x-1, 0), r = min(x+1, W-1)
+            const T uL = (x == 0) ? uC.e[e] : (e == 0 ? uLn : uC.e[e > 0 ? e - 1 : 0]);
+            const T vL = (x == 0) ? vC.e[e] : (e == 0 ? vLn : vC.e[e > 0 ? e - 1 : 0]);
+            const T uR = (x >= g.W - 1) ? uC.e[e] : (e == V - 1 ? uRn : uC.e[e < V - 1 ? e + 1 : e]);
+            const T vR = (x >= g.W - 1) ? vC.e[e] : (e == V - 1 ? vRn : vC.e[e < V - 1 ? e + 1 : e]);
+            const T dv_dx = cdiff<T, RECIP>(vR, vL, ph.ddx, ph.rdx);
+            const T du_dy = cdiff<T, RECIP>(uD.e[e], uU.e[e], ph.ddy, ph.rdy);
+            const T du_dx = cdiff<T, RECIP>(uR, uL, ph.ddx, ph.rdx);
+            const T dv_dy = cdiff<T, RECIP>(vD.e[e], vU.e[e], ph.ddy, ph.rdy);
+            zo.e[e] = A::sub(dv_dx, du_dy);
+            dv.e[e] = A::add(du_dx, dv_dy);
+        }
+        const long long o = lvl + row + x0;
+        if (x0 + V <= g.W) {
+            *reinterpret_cast<int4 *>(vort + o) = *reinterpret_cast<const int4 *>(zo.e);
+            *reinterpret_cast<int4 *>(dvg + o) = *reinterpret_cast<const int4 *>(dv.e);
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if (x0 + e < g.W) {
+                    vort[o + e] = zo.e[e];
+                    dvg[o + e] = dv.e[e];
+                }
+        }
+        // next row: at the last row of the domain "down" stays the row itself, which uN/vN already hold
+        uU = uC; vU = vC;
+        uC = uD; vC = vD;
+        uD = uN; vD = vN;
+    }
 }
 
 template <typename T>
@@ -184,9 +249,10 @@ cudaError_t launch_stage_direct(const Geometry<T> &g, const Physics<T> &ph, cons
 template <typename T>
 cudaError_t launch_diagnostics(const Geometry<T> &g, const Physics<T> &ph, const T *u, const T *v, T *vort, T *dvg,
                                cudaStream_t st) {
-    const dim3 grid = grid_for(g, g.H, g.W), block(kBX, kBY);
-    if (ph.recip) diagnostics_kernel<T, true><<<grid, block, 0, st>>>(g, ph, u, v, vort, dvg);
-    else diagnostics_kernel<T, false><<<grid, block, 0, st>>>(g, ph, u, v, vort, dvg);
+    constexpr int V = 16 / (int)sizeof(T);
+    const dim3 grid((g.W + kDiagThreads * V - 1) / (kDiagThreads * V), (g.H + kDiagRows - 1) / kDiagRows, g.L);
+    if (ph.recip) diagnostics_kernel<T, true><<<grid, kDiagThreads, 0, st>>>(g, ph, u, v, vort, dvg);
+    else diagnostics_kernel<T, false><<<grid, kDiagThreads, 0, st>>>(g, ph, u, v, vort, dvg);
     return cudaGetLastError();
 }
 
