@@ -424,7 +424,12 @@ public:
                 check(wsb_sim_run(sim_, chunk, &done));
             }
             remaining -= done;
-            if (done < chunk) stopped = true;  // max_time reached (:87-89)
+            // max_time reached (:87-89). `done < chunk` misses a stop on the LAST step of a chunk (e.g. the defaults:
+            // dt=0.01, max_time=10, interval=10 reach t >= 10 at step 1000, a chunk boundary), so the library's own
+            // clock is tested too -- against max_time as the library rounded it for the simulation's dtype
+            wsb_config lc;
+            check(wsb_sim_get_config(sim_, &lc));
+            if (done < chunk || wsb_sim_get_time(sim_) >= lc.max_time) stopped = true;
             if (om_ && interval > 0 && wsb_sim_get_step(sim_) % interval == 0) om_->write_output(*this);
             if (done == 0) break;
         }

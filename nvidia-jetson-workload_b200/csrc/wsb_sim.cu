@@ -357,6 +357,21 @@ static cudaError_t launch_step(const wsb_sim *s, const Geometry<T> &g, const Phy
                                     : launch_step_fused<T>(g, ph, a, s->nstages, st);
 }
 
+// Arguments of one whole-step launch from the current state to `next` (both callers: the device-resident step
+// and the streamed host step); row ranges are filled in by the caller.
+template <typename T>
+static StepArgs<T> step_args(const wsb_sim *s) {
+    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
+    StepArgs<T> a{};
+    a.Y = planes<const T>(s, cur3);
+    a.O = planes<T>(s, s->next);
+    a.dt = (T)s->dt;
+    a.half_dt = T(0.5f) * a.dt;  // `0.5f * dt_` (weather_simulation.cpp:249): one rounding
+    a.dt6 = a.dt / T(6.0f);      // `dt_ / 6.0f` (:438)
+    a.classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
+    return a;
+}
+
 // Whole-step kernels. Single GPU: one launch per step. Row slabs: the `halo` rows next to each slab edge
 // need the neighbours' ghost rows, the rest does not, so a step is
 //   edge stream (high priority): wait ghosts + previous interior -> ONE launch over both edge bands -> ev_edge
@@ -367,14 +382,7 @@ template <typename T>
 static int enqueue_step_fused(wsb_sim *s) {
     const Geometry<T> g = s->cur.geom<T>();
     const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
-    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
-    StepArgs<T> a{};
-    a.Y = planes<const T>(s, cur3);
-    a.O = planes<T>(s, s->next);
-    a.dt = (T)s->dt;
-    a.half_dt = T(0.5f) * a.dt;
-    a.dt6 = a.dt / T(6.0f);
-    a.classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
+    StepArgs<T> a = step_args<T>(s);
     const int H = s->cur.H;
     const int halo = s->nstages;  // one ghost row per fused stage
     if (!s->comm) {
@@ -804,6 +812,10 @@ int wsb_grid_device_pointer(wsb_grid *g, int32_t field, void **dev_ptr, int64_t 
     WSB_CUDA(cudaSetDevice(g->device));
     if (g->owner && field >= WSB_FIELD_VORTICITY) WSB_TRY(sim_materialize_diagnostics(g->owner));
     WSB_TRY(grid_materialize(g, field));
+    // the consumer reads on ITS stream: everything this library has enqueued for the grid (pending asynchronous
+    // steps, the fill of a lazily materialised field, the diagnostics kernel) must have completed first
+    if (g->owner) WSB_TRY(sim_sync(g->owner));
+    else WSB_CUDA(cudaStreamSynchronize(g->stream));
     *dev_ptr = g->origin(field);
     if (pitch_elems) *pitch_elems = g->pitch;
     return WSB_OK;
@@ -918,7 +930,10 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             st = fail(WSB_ERR_INVALID_ARGUMENT, "unknown kernel_variant");
             break;
         }
-        if (s->nrows < (is_step_path(s->path) ? s->nstages : 1) && c.nranks > 1) {
+        // every slab (this rank's AND its neighbours') must be at least as deep as the ghost band; tested on the
+        // smallest slab of the balanced partition, which all ranks know, so that every rank accepts or rejects the
+        // configuration identically BEFORE ncclCommInitRank (a rank failing alone would leave the others blocked)
+        if (c.nranks > 1 && c.grid_height / c.nranks < (is_step_path(s->path) ? s->nstages : 1)) {
             st = fail(WSB_ERR_INVALID_ARGUMENT, "row slab thinner than the ghost depth");
             break;
         }
@@ -1023,12 +1038,7 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
     const Geometry<T> geo = g->geom<T>();
     const Physics<T> ph = g->physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
     void *cur3[3] = {g->f[0].base, g->f[1].base, g->f[2].base};
-    StepArgs<T> a{};
-    a.Y = planes<const T>(s, cur3);
-    a.O = planes<T>(s, s->next);
-    a.dt = (T)s->dt;
-    a.half_dt = T(0.5f) * a.dt;
-    a.dt6 = a.dt / T(6.0f);
+    StepArgs<T> a = step_args<T>(s);
     // 16 slabs: the call ends one slab after the last upload ((1 + 1/n) x the transfer) and every slab costs about
     // 50-100 us of event / launch latency in the upload -> step -> download chain (profiles/r1/e2e_sweep*.txt)
     int want_slabs = 16;

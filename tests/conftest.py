@@ -24,8 +24,20 @@ def _gpu_count():
 
 
 def pytest_collection_modifyitems(config, items):
-    # -m gpu on a box without a GPU must fail loudly, not skip: the product has no CPU fallback.
-    pass
+    """`-m gpu` on a box without a usable CUDA device (or without the built extension) must FAIL loudly, not pass
+    by skipping: the product has no CPU fallback. Every selected gpu test gets a failing setup in that case."""
+    markexpr = (config.getoption("markexpr", "") or "").replace(" ", "")
+    if markexpr != "gpu" or _gpu_count() > 0:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None:
+            item.fixturenames.insert(0, "_wsb_no_gpu")
+
+
+@pytest.fixture
+def _wsb_no_gpu():
+    pytest.fail("pytest -m gpu needs a CUDA device and lib/libweather_b200.so (the product has no CPU fallback): "
+                "0 devices visible", pytrace=False)
 
 
 @pytest.fixture(scope="session")

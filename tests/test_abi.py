@@ -116,3 +116,18 @@ def test_header_is_valid_c_and_the_c_example_links():
     if _capi.device_count() == 0:  # fails loudly, no CPU fallback
         r = subprocess.run([exe, "64", "64", "2"], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_exact_reciprocal_kernels_contain_no_contracted_fma():
+    """Parity guard on the BUILT library: ptxas 12.9 was seen contracting packed mul + add into FFMA2
+    even under --fmad=false; profiles/check_no_fma.sh disassembles every exact-reciprocal kernel and fails on any
+    fused multiply-add that is not exact by construction. The Makefile runs the same script after linking."""
+    import shutil
+    import subprocess
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    env = dict(os.environ, PATH=os.environ.get("PATH", "") + ":/usr/local/cuda/bin")
+    r = subprocess.run([os.path.join(ROOT, "profiles", "check_no_fma.sh"), _capi.LIB_PATH], capture_output=True,
+                       text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "check_no_fma: ok" in r.stdout

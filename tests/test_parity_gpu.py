@@ -448,6 +448,28 @@ def test_step_host_streams_the_state_and_matches_the_oracle(integ, dtype):
     s.close()
 
 
+def test_step_host_honours_rk4_classical():
+    """The streamed host step and the device-resident step must run the SAME integrator on one handle: with the
+    textbook-RK4 opt-in both are the oracle's classical combine (the streamed path once silently used the aliased one)."""
+    W, H = 160, 700
+    u, v, h = syn.random_vorticity(W, H)
+    h = (h + syn.gaussian_bump(W, H)[2] - 10.0).astype(np.float32)
+    o = Oracle(W, H, 0, 2, rk4_classical=True, coriolis_f=0.1)
+    o.set_state(u, v, h)
+    o.step(2)
+    s = cuda_sim(W, H, 0, 2, "auto", rk4_classical=True, coriolis_f=0.1)
+    assert s.kernel_name == "step_fused_tma"
+    ou, ov, oh = s.step_host(u, v, h)
+    ou, ov, oh = s.step_host(ou, ov, oh)
+    for name, got in (("u", ou), ("v", ov), ("h", oh)):
+        assert_bit_equal(np.array(got), o.get_field(name), f"classical step_host {name}")
+    s.set_state(u, v, h)
+    s.step(2)
+    assert_bit_equal(s.get_field("h"), o.get_field("h"), "classical step")
+    s.close()
+    o.close()
+
+
 @pytest.mark.parametrize("kernel", VARIANTS)
 def test_subnormal_and_extreme_magnitudes(kernel):
     """No flush-to-zero anywhere (scalar and packed fp32x2 paths): fields in the subnormal range, mixed with

@@ -174,6 +174,45 @@ def test_python_output_manager_and_double_precision(ours):
     assert sim64.get_kernel_name() == "step_fused_tma"
 
 
+@pytest.mark.parametrize("interval", [10, 1, 7])
+def test_run_with_output_manager_stops_at_max_time_like_the_reference(ref, ours, interval):
+    """run() breaks right after the first step with time >= max_time (weather_simulation.cpp:87-89). With the
+    defaults (dt=0.01, max_time=10) that is step 1000 -- an output-interval boundary for interval 10 and 1, where the
+    shim's chunked run() must not start another chunk."""
+    c = make_config(ref, "ShallowWater", "ExplicitEuler", 16, 12)
+    c.max_time = 10.0
+    r = ref.WeatherSimulation(c)
+    r.initialize()
+    r.run(1200)
+    assert r.get_current_step() == 1000
+
+    writes = []
+
+    class Recorder(ours.OutputManager):
+        def initialize(self, sim):
+            pass
+
+        def write_output(self, sim):
+            writes.append(sim.get_current_step())
+
+        def finalize(self, sim):
+            pass
+
+    c = make_config(ours, "ShallowWater", "ExplicitEuler", 16, 12)
+    c.max_time = 10.0
+    c.output_interval = interval
+    s = ours.WeatherSimulation(c)
+    s.set_output_manager(Recorder())
+    s.initialize()
+    s.run(1200)
+    assert s.get_current_step() == r.get_current_step() == 1000
+    assert s.get_current_time() == r.get_current_time()
+    assert writes == list(range(interval, 1001, interval))
+    s.run(5)  # already past max_time: one more step, then the break (the check follows the step)
+    r.run(5)
+    assert s.get_current_step() == r.get_current_step() == 1001
+
+
 def test_csv_output_manager(ours, tmp_path):
     """The reference declares a CSV manager but never implements it; ours writes one file per interval."""
     from weather_sim.output import CSVOutputManager
