@@ -80,6 +80,15 @@ typedef enum wsb_rk4_mode {
     WSB_RK4_CLASSICAL = 1  /* textbook RK4 (non-parity opt-in) */
 } wsb_rk4_mode;
 
+/* Floating-point evaluation of the packed fp32 whole-step kernels. */
+typedef enum wsb_arith_mode {
+    WSB_ARITH_STRICT = 0, /* every operation of the reference, in its order: bit-identical for ALL inputs */
+    WSB_ARITH_FOLDED = 1  /* opt-in, fp32, dx == dy with 2dx a power of two: the exact scale 1/(2dx) is folded
+                             into the stage coefficients (6 fewer multiplies per cell-stage). Bit-identical
+                             to STRICT unless an intermediate of the reference is subnormal or within 2dx of
+                             overflow; the sign of a zero tendency may differ. Ignored where it does not apply. */
+} wsb_arith_mode;
+
 /* Which hand-written sm_100a path advances the state. All variants produce bit-identical results. */
 typedef enum wsb_kernel_variant {
     WSB_KERNEL_AUTO = 0,           /* best available for the configuration */
@@ -114,7 +123,8 @@ typedef struct wsb_config {
     int32_t rank;
     int32_t nranks;
     const void *nccl_unique_id; /* WSB_NCCL_UNIQUE_ID_BYTES bytes from wsb_nccl_get_unique_id on rank 0 */
-    int32_t reserved[8];
+    int32_t arith_mode;         /* wsb_arith_mode (0 = strict, the default) */
+    int32_t reserved[7];
 } wsb_config;
 
 #define WSB_NCCL_UNIQUE_ID_BYTES 128

@@ -72,12 +72,14 @@ __device__ __forceinline__ T rk4_combine(T y, T dt6, T k1, T k2, T k3, T k4) {
 
 }  // namespace wsb
 
-// ---- packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2, two IEEE operations per issue slot) -----------
+// ---- packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2, two IEEE operations per issue slot) -----
 // ptxas 12.9 contracts a packed multiply feeding a packed add/sub into FFMA2 even for mul.rn/add.rn and
-// even under --fmad=false, which would break bit parity. The rule used here therefore is:
-// every add/sub that consumes a product is issued as two SCALAR add.rn.f32 (never contracted), while
-// multiplies and the adds/subs of non-products are packed. The build checks that the RECIP kernels
-// contain no FFMA/FFMA2 at all (profiles/check_no_fma.sh).
+// even under --fmad=false, which would break bit parity. What it does NOT touch is an explicit
+// fma.rn.f32x2 whose multiplier is the constant -1: `c - p` for a product p is therefore issued as
+// fma(p, -1, c) = round((-p) + c), which IS the IEEE subtraction c - p, bit for bit (signed zeros included).
+// Sums `c + a*b` become c - ((-a)*b) with the sign carried by a constant factor ((-a)*b == -(a*b) exactly), so
+// every operation of the stencil is packed and none is contracted: the RECIP kernels contain FFMA2 only with
+// the immediate multiplier -1 (or 2, folded mode), checked on the built library by profiles/check_no_fma.sh.
 namespace wsb {
 
 struct F2 {
@@ -95,12 +97,12 @@ __device__ __forceinline__ F2 f2_unpack(unsigned long long v) {
     return r;
 }
 __device__ __forceinline__ F2 f2_splat(float v) { return F2{v, v}; }
-// packed: products, and sums/differences whose operands are not products
 __device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
     unsigned long long r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
     return f2_unpack(r);
 }
+// sums/differences whose operands are NOT products (safe from contraction)
 __device__ __forceinline__ F2 f2_sub_packed(F2 a, F2 b) {
     unsigned long long r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
@@ -111,19 +113,41 @@ __device__ __forceinline__ F2 f2_add_packed(F2 a, F2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
     return f2_unpack(r);
 }
-// scalar pairs: for sums/differences that consume a product
-__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { return F2{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
-__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) { return F2{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
-__device__ __forceinline__ F2 f2_neg(F2 a) { return F2{-a.x, -a.y}; }
+// c - p for a product p: fma(p, -1, c), exact and never contracted further
+__device__ __forceinline__ F2 f2_sub_prod(F2 c, F2 p) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(p)), "l"(0xBF800000BF800000ULL), "l"(f2_pack(c)));
+    return f2_unpack(r);
+}
+// c + 2*k: one FFMA2 with the immediate 2. Identical to c + round(2*k) unless 2*k overflows (folded mode only)
+__device__ __forceinline__ F2 f2_add_twice(F2 c, F2 k) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(k)), "l"(0x4000000040000000ULL), "l"(f2_pack(c)));
+    return f2_unpack(r);
+}
 
-// Constants of the packed path, splatted once per kernel.
+// Constants of the packed path, splatted once per kernel. The negated copies carry the signs (see above).
 struct PhysicsF2 {
-    F2 rdx, rdy, g, f;
+    F2 nrdx, rdy;  // -1/(2dx), 1/(2dy)
+    F2 g, ng, f, nf;
 };
 
-// tendency_cell for a pair of horizontally adjacent cells (x, y) = (cell 0, cell 1), exact-reciprocal
-// spacing only. uLft/uRgt... are the cells left of cell 0 and right of cell 1 (from the neighbouring lanes).
-// Same operation order as tendency_cell<float, true>: results are bit-identical.
+__device__ __forceinline__ PhysicsF2 physics_f2(const Physics<float> &ph) {
+    PhysicsF2 p;
+    p.nrdx = f2_splat(-ph.rdx);
+    p.rdy = f2_splat(ph.rdy);
+    p.g = f2_splat(ph.g);
+    p.ng = f2_splat(-ph.g);
+    p.f = f2_splat(ph.f);
+    p.nf = f2_splat(-ph.f);
+    return p;
+}
+
+// tendency_cell for a pair of horizontally adjacent cells (x, y) = (cell 0, cell 1), exact-reciprocal spacing
+// only. uLft/uRgt... are the cells left of cell 0 and right of cell 1 (from the neighbouring lanes). Every
+// operation is the reference's (weather_simulation.cpp:516-537), in its order; with nqx := -(q_x):
+//   (-u)*ux == u*nux,  g*hx == (-g)*nhx,  -(u*hx) == u*nhx,  a + f*v == a - (-f)*v      (all exact, signs included)
+// so the results are bit-identical to tendency_cell<float, true>.
 __device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F2 h, float uLft, float uRgt, F2 uU, F2 uD,
                                               float vLft, float vRgt, F2 vU, F2 vD, float hLft, float hRgt, F2 hU,
                                               F2 hD, F2 &du, F2 &dv, F2 &dh) {
@@ -131,25 +155,70 @@ __device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F
     const F2 dux = F2{__fsub_rn(u.y, uLft), __fsub_rn(uRgt, u.x)};
     const F2 dvx = F2{__fsub_rn(v.y, vLft), __fsub_rn(vRgt, v.x)};
     const F2 dhx = F2{__fsub_rn(h.y, hLft), __fsub_rn(hRgt, h.x)};
-    const F2 ux = f2_mul(dux, ph.rdx);
+    const F2 nux = f2_mul(dux, ph.nrdx);
     const F2 uy = f2_mul(f2_sub_packed(uD, uU), ph.rdy);
-    const F2 vx = f2_mul(dvx, ph.rdx);
+    const F2 nvx = f2_mul(dvx, ph.nrdx);
     const F2 vy = f2_mul(f2_sub_packed(vD, vU), ph.rdy);
-    const F2 hx = f2_mul(dhx, ph.rdx);
+    const F2 nhx = f2_mul(dhx, ph.nrdx);
     const F2 hy = f2_mul(f2_sub_packed(hD, hU), ph.rdy);
-    // ((((-u)*ux) - (v*uy)) - (g*hx)) + (f*v); (-u)*ux == -(u*ux) exactly
-    du = f2_add(f2_sub(f2_sub(f2_neg(f2_mul(u, ux)), f2_mul(v, uy)), f2_mul(ph.g, hx)), f2_mul(ph.f, v));
-    dv = f2_sub(f2_sub(f2_sub(f2_neg(f2_mul(u, vx)), f2_mul(v, vy)), f2_mul(ph.g, hy)), f2_mul(ph.f, u));
-    dh = f2_sub(f2_sub(f2_neg(f2_mul(h, f2_add(ux, vy))), f2_mul(u, hx)), f2_mul(v, hy));
+    // du = ((((-u)*ux) - (v*uy)) - (g*hx)) + (f*v)
+    du = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, nux), f2_mul(v, uy)), f2_mul(ph.ng, nhx)), f2_mul(ph.nf, v));
+    // dv = ((((-u)*vx) - (v*vy)) - (g*hy)) - (f*u)
+    dv = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, nvx), f2_mul(v, vy)), f2_mul(ph.g, hy)), f2_mul(ph.f, u));
+    // dh = (((-h)*(ux+vy)) - (u*hx)) - (v*hy);  ux + vy == vy - nux;  (-P) - Q == (-Q) - P
+    const F2 s = f2_sub_prod(vy, nux);
+    dh = f2_sub_prod(f2_sub_prod(f2_mul(u, nhx), f2_mul(h, s)), f2_mul(v, hy));
 }
 
-__device__ __forceinline__ F2 axpy_pair(F2 y, F2 c, F2 k) { return f2_add(y, f2_mul(c, k)); }
+// ---- folded mode (opt-in, WSB_ARITH_FOLDED): dx == dy and 2dx a power of two, r = 1/(2dx) ---------------------
+// Scaling by a power of two commutes with every rounding as long as nothing under- or overflows, so the six
+// multiplications by r are dropped: the tendencies are carried as K' = K/r (differences unscaled, f' = f/r) and r
+// is folded into the stage coefficients (c*r, dt6*r: exact). 32 instead of 38 operations per cell-stage.
+// Results are bit-identical to the strict path unless an intermediate of the reference is subnormal (the
+// reference then rounds (a-b)*r or a product at subnormal granularity, the folded form does not) or within a
+// factor 1/r of overflow; the sign of an exact zero tendency can differ (nD = L - R is +0, not -0, when L == R),
+// which is invisible unless a field holds -0. tests/test_parity_gpu.py states both bounds.
+struct PhysicsFold {
+    F2 g, ng, fs, nfs;  // fs = f/r
+};
 
-// y + dt6 * (((k1 + 2*k2) + 2*k3) + k4)
-__device__ __forceinline__ F2 rk4_combine_pair(F2 y, F2 dt6, F2 k1, F2 k2, F2 k3, F2 k4) {
-    const F2 two = f2_splat(2.0f);
-    const F2 s = f2_add_packed(f2_add(f2_add(k1, f2_mul(two, k2)), f2_mul(two, k3)), k4);
-    return f2_add(y, f2_mul(dt6, s));
+__device__ __forceinline__ PhysicsFold physics_fold(const Physics<float> &ph) {
+    PhysicsFold p;
+    p.g = f2_splat(ph.g);
+    p.ng = f2_splat(-ph.g);
+    p.fs = f2_splat(ph.f * ph.ddx);  // f / r, exact (ddx is a power of two)
+    p.nfs = f2_splat(-(ph.f * ph.ddx));
+    return p;
+}
+
+__device__ __forceinline__ void tendency_pair_folded(const PhysicsFold &ph, F2 u, F2 v, F2 h, float uLft, float uRgt,
+                                                     F2 uU, F2 uD, float vLft, float vRgt, F2 vU, F2 vD, float hLft,
+                                                     float hRgt, F2 hU, F2 hD, F2 &du, F2 &dv, F2 &dh) {
+    // negated horizontal differences L - R per cell (scalar), vertical differences D - U (packed)
+    const F2 ndux = F2{__fsub_rn(uLft, u.y), __fsub_rn(u.x, uRgt)};
+    const F2 ndvx = F2{__fsub_rn(vLft, v.y), __fsub_rn(v.x, vRgt)};
+    const F2 ndhx = F2{__fsub_rn(hLft, h.y), __fsub_rn(h.x, hRgt)};
+    const F2 duy = f2_sub_packed(uD, uU), dvy = f2_sub_packed(vD, vU), dhy = f2_sub_packed(hD, hU);
+    du = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, ndux), f2_mul(v, duy)), f2_mul(ph.ng, ndhx)), f2_mul(ph.nfs, v));
+    dv = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, ndvx), f2_mul(v, dvy)), f2_mul(ph.g, dhy)), f2_mul(ph.fs, u));
+    const F2 s = f2_sub_packed(dvy, ndux);
+    dh = f2_sub_prod(f2_sub_prod(f2_mul(u, ndhx), f2_mul(h, s)), f2_mul(v, dhy));
+}
+
+// y + dt6r * (((k1 + 2*k2) + 2*k3) + k4) on folded tendencies, ndt6r = -(dt6*r); 2*k folded into FFMA2
+__device__ __forceinline__ F2 rk4_combine_pair_folded(F2 y, F2 ndt6r, F2 k1, F2 k2, F2 k3, F2 k4) {
+    const F2 s = f2_add_packed(f2_add_twice(f2_add_twice(k1, k2), k3), k4);
+    return f2_sub_prod(y, f2_mul(ndt6r, s));
+}
+
+// y + c*k as y - (nc*k), nc = -c
+__device__ __forceinline__ F2 axpy_pair(F2 y, F2 nc, F2 k) { return f2_sub_prod(y, f2_mul(nc, k)); }
+
+// y + dt6 * (((k1 + 2*k2) + 2*k3) + k4), ndt6 = -dt6. 2*k as a product of its own (overflows like the reference's).
+__device__ __forceinline__ F2 rk4_combine_pair(F2 y, F2 ndt6, F2 k1, F2 k2, F2 k3, F2 k4) {
+    const F2 ntwo = f2_splat(-2.0f);
+    const F2 s = f2_add_packed(f2_sub_prod(f2_sub_prod(k1, f2_mul(ntwo, k2)), f2_mul(ntwo, k3)), k4);
+    return f2_sub_prod(y, f2_mul(ndt6, s));
 }
 
 }  // namespace wsb

@@ -94,6 +94,7 @@ struct StepArgs {
     Planes3<T> O;         // y_{n+1}
     T dt, half_dt, dt6;
     int classical;
+    int fold;              // WSB_ARITH_FOLDED requested (used where the kernel and the spacing allow it)
     int y_begin, y_end;    // local OUTPUT row range this launch covers
     int y_begin2, y_end2;  // optional second range in the same launch (slab top + bottom edges); empty if equal
     int rows_per_chunk;    // rows each warp sweeps; 0 = library default

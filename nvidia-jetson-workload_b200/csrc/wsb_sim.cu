@@ -369,6 +369,7 @@ static StepArgs<T> step_args(const wsb_sim *s) {
     a.half_dt = T(0.5f) * a.dt;  // `0.5f * dt_` (weather_simulation.cpp:249): one rounding
     a.dt6 = a.dt / T(6.0f);      // `dt_ / 6.0f` (:438)
     a.classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
+    a.fold = s->cfg.arith_mode == WSB_ARITH_FOLDED;
     return a;
 }
 
@@ -864,6 +865,10 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
     if (c.model < 0 || c.model > WSB_MODEL_GENERAL) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown model");
     if (c.integration_method < 0 || c.integration_method > WSB_INT_SEMI_IMPLICIT)
         return fail(WSB_ERR_INVALID_ARGUMENT, "unknown integration method");
+    if (c.arith_mode != WSB_ARITH_STRICT && c.arith_mode != WSB_ARITH_FOLDED)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "unknown arith_mode");
+    if (const char *e = std::getenv("WSB_ARITH"))  // A/B runs: WSB_ARITH=folded|strict overrides the configuration
+        c.arith_mode = std::strcmp(e, "folded") == 0 ? WSB_ARITH_FOLDED : WSB_ARITH_STRICT;
     if (c.nranks < 1) c.nranks = 1;
     if (c.rank < 0 || c.rank >= c.nranks) return fail(WSB_ERR_INVALID_ARGUMENT, "rank out of range");
     if (c.nranks > 1 && c.num_levels != 1)

@@ -142,7 +142,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <typename T, int NST, int V, bool RECIP, bool CL>
+template <typename T, int NST, int V, bool RECIP, bool CL, bool FOLD>
 struct SweepT {
     using L = Layout<T, NST, V>;
     using Windows = Row<T, V>[(NST > 1 ? NST - 1 : 1)][3];
@@ -155,7 +155,9 @@ struct SweepT {
     const Geometry<T> &g;
     const Physics<T> &ph;
     const StepArgs<T> &a;
-    PhysicsF2 ph2;  // splatted constants of the packed path
+    PhysicsF2 ph2;    // splatted constants of the packed path
+    PhysicsFold phf;  // ... of its folded variant (wsb_arith.cuh)
+    float rs;         // FOLD: r = 1/(2dx), folded into every stage coefficient; else unused
     const CUtensorMap *tm_u, *tm_v, *tm_h;  // tiled-TMA descriptors of the y_n planes (kernel parameters)
     int lane, c0, xs;
     bool edge_strip, fix_left, fix_right;
@@ -278,8 +280,12 @@ struct SweepT {
                     rg[f] = (p == V / 2 - 1) ? (float)Rgt[f] : (float)C.f[f][2 * p + 2];
                 }
                 F2 du, dv, dh;
-                tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1], rg[1],
-                              P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
+                if constexpr (FOLD)
+                    tendency_pair_folded(phf, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1],
+                                         rg[1], P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
+                else
+                    tendency_pair(ph2, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1], rg[1],
+                                  P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
                 k.f[0][2 * p] = du.x; k.f[0][2 * p + 1] = du.y;
                 k.f[1][2 * p] = dv.x; k.f[1][2 * p + 1] = dv.y;
                 k.f[2][2 * p] = dh.x; k.f[2][2 * p + 1] = dh.y;
@@ -366,7 +372,7 @@ struct SweepT {
             const T c = (NST == 4 && S1 == 3) ? a.dt : a.half_dt;
             Row<T, V> &t = Lv[S1 - 1][m3];
             if constexpr (kPacked) {
-                const F2 c2 = f2_splat((float)c);
+                const F2 c2 = f2_splat(FOLD ? -((float)c * rs) : -(float)c);  // axpy_pair takes the negated coefficient
 #pragma unroll
                 for (int f = 0; f < 3; ++f)
 #pragma unroll
@@ -422,15 +428,17 @@ struct SweepT {
                 ld_k(k2, k2s, m3);
                 // reference aliasing: "k1" reads k4 at the combine (weather_simulation.cpp:350-351, F5)
                 if constexpr (kPacked) {
-                    const F2 dt6 = f2_splat((float)a.dt6);
+                    const F2 dt6 = f2_splat(FOLD ? -((float)a.dt6 * rs) : -(float)a.dt6);  // negated, see rk4_combine_pair
 #pragma unroll
                     for (int f = 0; f < 3; ++f)
 #pragma unroll
                         for (int p = 0; p < V; p += 2) {
                             const F2 k4 = F2{(float)k.f[f][p], (float)k.f[f][p + 1]};
-                            const F2 rr = rk4_combine_pair(F2{(float)yb.f[f][p], (float)yb.f[f][p + 1]}, dt6, k4,
-                                                           F2{(float)k2.f[f][p], (float)k2.f[f][p + 1]},
-                                                           F2{(float)k3.f[f][p], (float)k3.f[f][p + 1]}, k4);
+                            const F2 yy = F2{(float)yb.f[f][p], (float)yb.f[f][p + 1]};
+                            const F2 kk2 = F2{(float)k2.f[f][p], (float)k2.f[f][p + 1]};
+                            const F2 kk3 = F2{(float)k3.f[f][p], (float)k3.f[f][p + 1]};
+                            const F2 rr = FOLD ? rk4_combine_pair_folded(yy, dt6, k4, kk2, kk3, k4)
+                                               : rk4_combine_pair(yy, dt6, k4, kk2, kk3, k4);
                             o.f[f][p] = rr.x; o.f[f][p + 1] = rr.y;
                         }
                 } else {
@@ -442,7 +450,7 @@ struct SweepT {
                 }
                 }
             } else if constexpr (kPacked) {
-                const F2 dt2 = f2_splat((float)a.dt);
+                const F2 dt2 = f2_splat(FOLD ? -((float)a.dt * rs) : -(float)a.dt);
 #pragma unroll
                 for (int f = 0; f < 3; ++f)
 #pragma unroll
@@ -523,7 +531,7 @@ struct SweepT {
     }
 };
 
-template <typename T, int NST, int V, bool RECIP, int MINB, bool CL>
+template <typename T, int NST, int V, bool RECIP, int MINB, bool CL, bool FOLD>
 __global__ void __launch_bounds__(32, MINB)
     step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk,
                     const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
@@ -540,11 +548,12 @@ __global__ void __launch_bounds__(32, MINB)
     const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
     if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform
 
-    SweepT<T, NST, V, RECIP, CL> sw(g, ph, a);
-    sw.ph2.rdx = f2_splat((float)ph.rdx);
-    sw.ph2.rdy = f2_splat((float)ph.rdy);
-    sw.ph2.g = f2_splat((float)ph.g);
-    sw.ph2.f = f2_splat((float)ph.f);
+    SweepT<T, NST, V, RECIP, CL, FOLD> sw(g, ph, a);
+    if constexpr (std::is_same<T, float>::value) {
+        sw.ph2 = physics_f2(ph);
+        sw.phf = physics_fold(ph);
+        sw.rs = ph.rdx;
+    }
     sw.tm_u = &tm_u;
     sw.tm_v = &tm_v;
     sw.tm_h = &tm_h;
@@ -655,13 +664,20 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     if (cudaError_t e = make_plane_map<T>(&th, g, a.Y.h, L::SW)) return e;
     if constexpr (NST == 4) {
         if (a.classical) {  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
-            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
-            else step_tma_kernel<T, NST, V, false, MINB, true><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
+            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true, false><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
+            else step_tma_kernel<T, NST, V, false, MINB, true, false><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
             return cudaGetLastError();
         }
     }
-    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
-    else step_tma_kernel<T, NST, V, false, MINB, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
+    if constexpr (std::is_same<T, float>::value && V % 2 == 0) {
+        // folded arithmetic (opt-in): one spacing, exact reciprocal, coefficients that stay normal after scaling
+        if (a.fold && ph.recip && ph.rdx == ph.rdy) {
+            step_tma_kernel<T, NST, V, true, MINB, false, true><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
+            return cudaGetLastError();
+        }
+    }
+    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
+    else step_tma_kernel<T, NST, V, false, MINB, false, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
     return cudaGetLastError();
 }
 

@@ -26,6 +26,7 @@ INTEGRATOR = {"euler": 0, "rk2": 1, "rk4": 2, "adams_bashforth": 3, "semi_implic
 FIELD = {"u": 0, "v": 1, "h": 2, "height": 2, "p": 3, "pressure": 3, "t": 4, "temperature": 4, "q": 5,
          "humidity": 5, "vorticity": 6, "divergence": 7}
 KERNEL = {"auto": 0, "stage_direct": 1, "step_fused_reg": 2, "step_fused_tma": 3, "step_fused": 3}
+ARITH = {"strict": 0, "folded": 1}
 
 
 class wsb_config(ctypes.Structure):
@@ -49,7 +50,8 @@ class wsb_config(ctypes.Structure):
         ("rank", ctypes.c_int32),
         ("nranks", ctypes.c_int32),
         ("nccl_unique_id", ctypes.c_void_p),
-        ("reserved", ctypes.c_int32 * 8),
+        ("arith_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 7),
     ]
 
 
@@ -347,7 +349,7 @@ class Simulation:
 
     def __init__(self, width, height, model="shallow_water", integrator="rk4", dx=1.0, dy=1.0, dt=0.01,
                  gravity=9.81, coriolis_f=0.0, max_time=10.0, dtype=np.float32, num_levels=1, device_id=0,
-                 rk4_classical=False, kernel="auto", rank=0, nranks=1, nccl_id=None):
+                 rk4_classical=False, kernel="auto", rank=0, nranks=1, nccl_id=None, arith="strict"):
         self._lib = load_library()
         cfg = wsb_config()
         cfg.struct_size = ctypes.sizeof(wsb_config)
@@ -361,6 +363,7 @@ class Simulation:
         cfg.rk4_mode = 1 if rk4_classical else 0
         cfg.kernel_variant = KERNEL[kernel] if isinstance(kernel, str) else int(kernel)
         cfg.rank, cfg.nranks = rank, nranks
+        cfg.arith_mode = ARITH[arith] if isinstance(arith, str) else int(arith)
         self._id_buf = None
         if nranks > 1:
             self._id_buf = ctypes.create_string_buffer(bytes(nccl_id), NCCL_UNIQUE_ID_BYTES)

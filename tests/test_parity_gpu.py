@@ -43,8 +43,9 @@ def cuda_sim(W, H, model=0, integ=2, kernel="auto", **kw):
 def compare_with_oracle(W, H, model, integ, kernel, steps, ic, dtype=np.float32, fields=("u", "v", "h", "vorticity"),
                         **phys):
     u, v, h = ic
+    arith = phys.pop("arith", "strict")  # a knob of the CUDA path only
     o = Oracle(W, H, model, integ, dtype=dtype, **phys)
-    s = cuda_sim(W, H, model, integ, kernel, dtype=dtype, **phys)
+    s = cuda_sim(W, H, model, integ, kernel, dtype=dtype, arith=arith, **phys)
     o.set_state(u, v, h)
     s.set_state(u, v, h)
     o.step(steps)
@@ -466,6 +467,74 @@ def test_step_host_honours_rk4_classical():
     s.set_state(u, v, h)
     s.step(2)
     assert_bit_equal(s.get_field("h"), o.get_field("h"), "classical step")
+    s.close()
+    o.close()
+
+
+# ---------------------------------------------------------------------- folded arithmetic (opt-in) --
+@pytest.mark.parametrize("integ", [0, 1, 2])
+@pytest.mark.parametrize("spacing", [1.0, 0.5, 4.0])
+def test_folded_arithmetic_is_bit_identical_on_normal_range_data(integ, spacing):
+    """WSB_ARITH_FOLDED drops the six exact multiplications by 1/(2dx) per cell-stage (the scale is folded into the
+    stage coefficients). While no intermediate is subnormal that commutes with every rounding: same bits as the
+    oracle, ragged shapes included."""
+    for W, H in ((200, 210), (57, 131), (8, 5)):
+        u, v, h = syn.random_vorticity(W, H)
+        h = (h + syn.gaussian_bump(W, H)[2] - 10.0).astype(np.float32)
+        o = Oracle(W, H, 0, integ, coriolis_f=0.1, dx=spacing, dy=spacing)
+        s = cuda_sim(W, H, 0, integ, "step_fused_tma", coriolis_f=0.1, dx=spacing, dy=spacing, arith="folded")
+        o.set_state(u, v, h)
+        s.set_state(u, v, h)
+        o.step(7)
+        s.step(7)
+        for n in ("u", "v", "h", "vorticity"):
+            assert_bit_equal(s.get_field(n), o.get_field(n), f"folded {W}x{H} i{integ} d{spacing} {n}")
+        s.close()
+        o.close()
+
+
+def test_folded_arithmetic_1024_200_steps_and_fallbacks():
+    W = H = 1024
+    u, v, h = syn.gaussian_bump(W, H)
+    o = Oracle(W, H, 0, 2, coriolis_f=0.1)
+    s = cuda_sim(W, H, 0, 2, "auto", coriolis_f=0.1, arith="folded")
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    o.step(200)
+    s.step(200)
+    for n in ("u", "v", "h"):
+        assert_bit_equal(s.get_field(n), o.get_field(n), f"folded 1024 rk4 {n}")
+    s.close()
+    o.close()
+    # where folding does not apply (dx != dy, true division, fp64, the per-stage path) the flag is ignored: strict results
+    ic = syn.random_vorticity(96, 64)
+    compare_with_oracle(96, 64, 0, 2, "step_fused_tma", 3, ic, dx=1.0, dy=2.0, arith="folded")
+    compare_with_oracle(96, 64, 0, 2, "step_fused_tma", 3, ic, dx=0.7, dy=0.7, arith="folded")
+    compare_with_oracle(96, 64, 0, 2, "stage_direct", 3, ic, arith="folded")
+    compare_with_oracle(96, 64, 0, 1, "step_fused_tma", 3, tuple(a.astype(np.float64) for a in ic), dtype=np.float64,
+                        arith="folded")
+
+
+def test_folded_arithmetic_subnormal_bound():
+    """Where the reference itself rounds at subnormal granularity the folded form does not: the difference is bounded
+    by a few units of 2^-149 per operation -- far inside the north-star tolerance (rel-L2 <= 1e-5), and the strict
+    default stays bit-exact on the same input (test_subnormal_and_extreme_magnitudes)."""
+    W, H = 120, 40
+    rng = np.random.default_rng(99)
+    base = rng.uniform(-1.0, 1.0, (3, H, W))
+    scale = np.where(rng.random((H, W)) < 0.5, 1e-40, 1.0)
+    u, v, h = ((base[k] * scale).astype(np.float32) for k in range(3))
+    o = Oracle(W, H, 0, 2, coriolis_f=0.1)
+    s = cuda_sim(W, H, 0, 2, "step_fused_tma", coriolis_f=0.1, arith="folded")
+    o.set_state(u, v, h)
+    s.set_state(u, v, h)
+    with np.errstate(all="ignore"):
+        o.step(3)
+    s.step(3)
+    for n in ("u", "v", "h"):
+        a, b = s.get_field(n).astype(np.float64), o.get_field(n).astype(np.float64)
+        assert np.abs(a - b).max() <= 1e-38, n          # absolute: a handful of subnormal ulps, amplified by O(1)
+        assert syn.rel_l2(a, b) <= 1e-5, n
     s.close()
     o.close()
 
