@@ -262,6 +262,13 @@ WSB_API const char *wsb_sim_kernel_name(const wsb_sim *sim);
  * energy = sum 0.5*h*(u^2+v^2) + 0.5*g*h^2 (SURVEY.md section 8d conservation checks). */
 WSB_API int wsb_sim_mass_energy(wsb_sim *sim, double *mass, double *energy);
 
+/* Measurement aid for the ghost-row phase (no counterpart in the reference, which has no
+ * decomposition): `reps` bare exchanges of the current state's ghost rows -- the very ncclSend/ncclRecv group a step
+ * issues, without any compute -- timed with CUDA events on the comm stream after a device-side rendezvous of the
+ * ranks. bytes_per_neighbour = ghost depth x 3 fields x row pitch. Single-rank simulations report 0 us. */
+WSB_API int wsb_sim_time_halo_exchange(wsb_sim *sim, int32_t reps, double *us_per_exchange,
+                                       int64_t *bytes_per_neighbour);
+
 /* ------------------------------------------------- initial conditions -- */
 
 /* The reference's InitialCondition::initialize(grid) family (initial_conditions.cpp:59-535), evaluated

@@ -150,6 +150,7 @@ int nccl_get_unique_id(void *out128);
 struct HaloComm;  // opaque: communicator + neighbour ranks
 int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out);
 void halo_comm_destroy(HaloComm *c);
+int halo_align(HaloComm *c, cudaStream_t st);
 // Exchange `nrows` boundary rows of each of the `nplanes` planes with the up/down neighbours:
 // sends local rows [0,nrows) up and [H-nrows,H) down; receives into ghost rows [-nrows,0) and [H,H+nrows).
 int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_size, int pitch, int H, int nrows,

@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
     const char *(*GetErrorString)(ncclResult_t);
@@ -56,6 +57,7 @@ int nccl_load(const NcclApi **api) {
             g_api.CommDestroy = (decltype(g_api.CommDestroy))sym("ncclCommDestroy");
             g_api.Send = (decltype(g_api.Send))sym("ncclSend");
             g_api.Recv = (decltype(g_api.Recv))sym("ncclRecv");
+            g_api.AllReduce = (decltype(g_api.AllReduce))sym("ncclAllReduce");
             g_api.GroupStart = (decltype(g_api.GroupStart))sym("ncclGroupStart");
             g_api.GroupEnd = (decltype(g_api.GroupEnd))sym("ncclGroupEnd");
             g_api.GetErrorString = (decltype(g_api.GetErrorString))sym("ncclGetErrorString");
@@ -92,6 +94,7 @@ struct HaloComm {
     const NcclApi *api = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    float *scratch = nullptr;  // one float on the device for halo_align
 };
 
 int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out) {
@@ -108,6 +111,12 @@ int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out
         delete c;
         return nccl_fail(api, r, "ncclCommInitRank");
     }
+    if (cudaMalloc(&c->scratch, sizeof(float)) != cudaSuccess || cudaMemset(c->scratch, 0, sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        api->CommDestroy(c->comm);
+        delete c;
+        return fail(WSB_ERR_CUDA, "cudaMalloc(halo scratch) failed");
+    }
     *out = c;
     return WSB_OK;
 }
@@ -115,7 +124,16 @@ int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out
 void halo_comm_destroy(HaloComm *c) {
     if (!c) return;
     if (c->comm) c->api->CommDestroy(c->comm);
+    if (c->scratch) cudaFree(c->scratch);
     delete c;
+}
+
+// A device-side rendezvous of all ranks on `st` (a one-float all-reduce): what follows on the stream starts within
+// microseconds on every GPU, whatever the host-side skew between the processes was.
+int halo_align(HaloComm *c, cudaStream_t st) {
+    const NcclApi *api = c->api;
+    WSB_NCCL(api, api->AllReduce(c->scratch, c->scratch, 1, ncclFloat, ncclSum, c->comm, st));
+    return WSB_OK;
 }
 
 int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_size, int pitch, int H, int nrows,

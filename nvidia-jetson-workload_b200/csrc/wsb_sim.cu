@@ -213,7 +213,7 @@ struct wsb_sim {
     cudaEvent_t ev_up[kMaxSlabs] = {}, ev_done[kMaxSlabs] = {};
     cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr, ev_interior = nullptr;
-    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_align = nullptr;
     bool run_open = false;    // ev_start recorded, ev_stop pending
     double last_run_ms = 0.0;
     wsb_metrics metrics{};
@@ -392,6 +392,17 @@ static int enqueue_step_fused(wsb_sim *s) {
         s->metrics.kernel_launches += 1;
         return WSB_OK;
     }
+    static const bool no_exchange = [] {  // timing diagnostics ONLY: results are wrong next to the slab seams
+        const bool v = std::getenv("WSB_DEBUG_NO_EXCHANGE") != nullptr;
+        if (v) std::fprintf(stderr, "[wsb] WSB_DEBUG_NO_EXCHANGE: ghost rows are NOT exchanged -- timing diagnostics only\n");
+        return v;
+    }();
+    if (no_exchange) {
+        a.y_begin = 0; a.y_end = H;
+        WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+        return WSB_OK;
+    }
     // dependencies captured BEFORE this step re-records the events
     WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_interior, 0));  // previous step's interior rows
     WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_halo, 0));      // ghost rows of the current state
@@ -475,8 +486,19 @@ static int sim_enqueue_step(wsb_sim *s) {
     return WSB_OK;
 }
 
-static int sim_begin_timing(wsb_sim *s) {
+// `align`: with row slabs, rendezvous all ranks on the device first (one-float all-reduce on the comm stream, which
+// the stepping streams wait for), so that the timed region of a multi-step run starts within microseconds on every
+// GPU instead of carrying the host-side skew between the processes into the first ghost exchanges.
+static int sim_begin_timing(wsb_sim *s, bool align = false) {
     if (!s->run_open) {
+        if (align && s->comm) {
+            WSB_TRY(sim_ensure_halo(s));
+            WSB_CUDA(cudaEventRecord(s->ev_align, s->stream));
+            WSB_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_align, 0));
+            WSB_TRY(halo_align(s->comm, s->comm_stream));
+            WSB_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));  // also still "ghost rows are valid"
+            WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        }
         WSB_CUDA(cudaEventRecord(s->ev_start, s->stream));
         s->run_open = true;
     }
@@ -834,7 +856,7 @@ static void sim_free(wsb_sim *s) {
         if (s->alt[k].base) cudaFree(s->alt[k].base);
     if (s->d_partial) cudaFree(s->d_partial);
     grid_fini(&s->cur);
-    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior};
+    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior, s->ev_align};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
@@ -911,7 +933,8 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         if (st != WSB_OK) break;
         s->cur.owner = s;
         for (int k = 0; k < WSB_NUM_FIELDS; ++k) s->alt[k].uniform = (double)kResetValue[k];
-        cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1, &s->ev_interior};
+        cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1, &s->ev_interior,
+                              &s->ev_align};
         for (cudaEvent_t *e : evs)
             if (cudaEventCreate(e) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
         if (st != WSB_OK) break;
@@ -1008,7 +1031,7 @@ wsb_grid *wsb_sim_current_grid(wsb_sim *s) { return s ? &s->cur : nullptr; }
 int wsb_sim_advance_async(wsb_sim *s, int32_t num_steps) {
     if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
     WSB_CUDA(cudaSetDevice(s->cur.device));
-    WSB_TRY(sim_begin_timing(s));
+    WSB_TRY(sim_begin_timing(s, num_steps > 1));
     for (int i = 0; i < num_steps; ++i) WSB_TRY(sim_enqueue_step(s));
     return WSB_OK;
 }
@@ -1182,7 +1205,7 @@ int wsb_sim_run(wsb_sim *s, int32_t num_steps, int32_t *steps_done) {
     if (num_steps <= 0) return WSB_OK;  // weather_simulation.cpp:69-71
     WSB_CUDA(cudaSetDevice(s->cur.device));
     const auto t0 = std::chrono::steady_clock::now();
-    WSB_TRY(sim_begin_timing(s));
+    WSB_TRY(sim_begin_timing(s, num_steps > 1));
     int done = 0;
     for (int i = 0; i < num_steps; ++i) {
         WSB_TRY(sim_enqueue_step(s));
@@ -1259,6 +1282,32 @@ const char *wsb_sim_kernel_name(const wsb_sim *s) {
         case PATH_STEP_TMA: return "step_fused_tma";
         default: return "stage_direct";
     }
+}
+
+int wsb_sim_time_halo_exchange(wsb_sim *s, int32_t reps, double *us_per_exchange, int64_t *bytes_per_neighbour) {
+    if (!s || !us_per_exchange) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *us_per_exchange = 0.0;
+    const int depth = is_step_path(s->path) ? s->nstages : 1;
+    if (bytes_per_neighbour) *bytes_per_neighbour = (int64_t)depth * 3 * s->cur.pitch * (int64_t)elem_size(s->dtype);
+    if (!s->comm || reps <= 0) return WSB_OK;
+    WSB_TRY(sim_sync(s));
+    void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
+    void *origins[3] = {plane_origin(s, cur3[0]), plane_origin(s, cur3[1]), plane_origin(s, cur3[2])};
+    const size_t es = elem_size(s->dtype);
+    // the first exchanges absorb the skew between the ranks; the all-reduce pins the start of the timed ones
+    for (int i = 0; i < 3; ++i)
+        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->comm_stream));
+    WSB_TRY(halo_align(s->comm, s->comm_stream));
+    WSB_CUDA(cudaEventRecord(s->ev_h0, s->comm_stream));
+    for (int i = 0; i < reps; ++i)
+        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->comm_stream));
+    WSB_CUDA(cudaEventRecord(s->ev_h1, s->comm_stream));
+    WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
+    float ms = 0.f;
+    WSB_CUDA(cudaEventElapsedTime(&ms, s->ev_h0, s->ev_h1));
+    *us_per_exchange = 1.0e3 * ms / reps;
+    s->halo_valid = true;  // exchanging the current state is idempotent
+    return WSB_OK;
 }
 
 int wsb_sim_mass_energy(wsb_sim *s, double *mass, double *energy) {

@@ -173,6 +173,10 @@ struct SweepT {
 
     // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
     static constexpr bool kPacked = std::is_same<T, float>::value && V % 2 == 0 && RECIP;
+#ifndef WSB_STEADY_BODY
+#define WSB_STEADY_BODY 1
+#endif
+    static constexpr bool kSteadyBody = WSB_STEADY_BODY != 0;
 
     __device__ __forceinline__ SweepT(const Geometry<T> &g_, const Physics<T> &ph_, const StepArgs<T> &a_)
         : g(g_), ph(ph_), a(a_) {}
@@ -320,16 +324,32 @@ struct SweepT {
         }
     }
 
+    // Steady state of the boundary-free body: every lane is entirely inside or outside the output range (interior
+    // strips are never ragged), so the row goes out as three PREDICATED vector stores -- no branch, the loop body
+    // stays one basic block.
+    __device__ __forceinline__ void store_out_predicated(const Row<T, V> &o, T *const (&po)[3]) const {
+        if constexpr (std::is_same<T, float>::value && V == 2) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(po[f]),
+                             "f"((float)o.f[f][0]), "f"((float)o.f[f][1]), "r"((unsigned)st_vec)
+                             : "memory");
+        } else {
+            store_out(o, po);
+        }
+    }
+
     // Stage S1 (1-based) at iteration n; PH = n % 3. Center row index m = n - S1.
     // PURE: the CTA is nowhere near a domain edge (interior strip, every row it loads is a real row): no boundary
     // handling is compiled in at all, pipeline-fill iterations just compute on garbage that is never stored.
-    template <int PH, int S1, bool PURE>
+    // STEADY (PURE only): the pipeline is full and the triple is complete -- no test of any kind in the body.
+    template <int PH, int S1, bool PURE, bool STEADY>
     __device__ __forceinline__ void stage(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool FAST_,
                                           T *const (&po)[3]) const {
         const bool FAST = PURE || FAST_;
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
-        if constexpr (PURE && S1 > 1) {
+        if constexpr (PURE && S1 > 1 && !STEADY) {
             // pipeline fill: the kernel is fp32-pipe bound, the 20 useless stage-rows per 64-row chunk are worth a
             // uniform branch per stage (stage 1 always runs: it also loads the y row into the carried window)
             if (n < 2 * S1) return;
@@ -465,18 +485,19 @@ struct SweepT {
 #pragma unroll
                     for (int e = 0; e < V; ++e) o.f[f][e] = axpy<T>(yb.f[f][e], a.dt, k.f[f][e]);
             }
-            if (!PURE || n >= 2 * NST) store_out(o, po);
+            if constexpr (STEADY) store_out_predicated(o, po);
+            else if (!PURE || n >= 2 * NST) store_out(o, po);
         }
     }
 
-    template <int PH, bool PURE>
+    template <int PH, bool PURE, bool STEADY = false>
     __device__ __forceinline__ void iteration(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool fast,
                                               T *(&po)[3]) const {
-        stage<PH, 1, PURE>(Lv, Yw, n, G, fast, po);
-        if constexpr (NST >= 2) stage<PH, 2, PURE>(Lv, Yw, n, G, fast, po);
+        stage<PH, 1, PURE, STEADY>(Lv, Yw, n, G, fast, po);
+        if constexpr (NST >= 2) stage<PH, 2, PURE, STEADY>(Lv, Yw, n, G, fast, po);
         if constexpr (NST >= 4) {
-            stage<PH, 3, PURE>(Lv, Yw, n, G, fast, po);
-            stage<PH, 4, PURE>(Lv, Yw, n, G, fast, po);
+            stage<PH, 3, PURE, STEADY>(Lv, Yw, n, G, fast, po);
+            stage<PH, 4, PURE, STEADY>(Lv, Yw, n, G, fast, po);
         }
 #pragma unroll
         for (int f = 0; f < 3; ++f) po[f] += g.pitch;
@@ -514,6 +535,14 @@ struct SweepT {
             const int grp_next = grp == kGroups - 1 ? 0 : grp + 1;
             wait_group(q, grp, parity);
             const bool fast = PURE || (unsigned)(n - n_lo) < n_span;
+            if (PURE && kSteadyBody && n > 2 * NST && n + 2 < niter) {
+                // boundary-free body, pipeline full, complete triple: three straight-line iterations (the only
+                // branches left per triple are the mbarrier wait, the producer election and the loop itself)
+                iteration<0, PURE, PURE>(Lv, Yw, n, G, true, po);
+                refill(q, grp_next);
+                iteration<1, PURE, PURE>(Lv, Yw, n + 1, G, true, po);
+                iteration<2, PURE, PURE>(Lv, Yw, n + 2, G, true, po);
+            } else {
             // general body: one code path for steady state and boundaries, the boundary tests are skipped by
             // uniform branches in the steady state
             iteration<0, PURE>(Lv, Yw, n, G, fast, po);
@@ -521,6 +550,7 @@ struct SweepT {
             if ((!PURE && fast) || n + 1 < niter) iteration<1, PURE>(Lv, Yw, n + 1, G, fast, po);
             else { po[0] += g.pitch; po[1] += g.pitch; po[2] += g.pitch; }
             if ((!PURE && fast) || n + 2 < niter) iteration<2, PURE>(Lv, Yw, n + 2, G, fast, po);
+            }
             if (grp_next == 0) parity ^= 1u;
             grp = grp_next;
             const T *t = G.c;  // rotate: triple q+1 lives where triple q-2 lived

@@ -142,6 +142,7 @@ SIGNATURES = {
     "wsb_sim_local_rows": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "wsb_sim_kernel_name": (ctypes.c_char_p, [_vp]),
     "wsb_sim_mass_energy": (ctypes.c_int, [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]),
+    "wsb_sim_time_halo_exchange": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_dbl), ctypes.POINTER(_i64)]),
     "wsb_ic_apply": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_dbl), _i32, ctypes.c_uint32, ctypes.c_char_p]),
     "wsb_ic_fill_host": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_dbl), _i32, ctypes.c_uint32, ctypes.c_char_p,
                                         _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -468,6 +469,12 @@ class Simulation:
         m, e = ctypes.c_double(), ctypes.c_double()
         _check(self._lib.wsb_sim_mass_energy(self._h, ctypes.byref(m), ctypes.byref(e)))
         return m.value, e.value
+
+    def time_halo_exchange(self, reps=100):
+        """(microseconds per bare ghost-row exchange, bytes per neighbour per direction); (0, bytes) on one rank."""
+        us, nbytes = ctypes.c_double(), ctypes.c_int64()
+        _check(self._lib.wsb_sim_time_halo_exchange(self._h, int(reps), ctypes.byref(us), ctypes.byref(nbytes)))
+        return us.value, nbytes.value
 
     def close(self):
         if getattr(self, "_h", None):

@@ -104,6 +104,10 @@ def _load_ref():
         lib.wsref_diagnostics.restype = None
         lib.wsref_apply_ic.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         lib.wsref_apply_ic.restype = ctypes.c_int
+        lib.wsref_set_omp_threads.argtypes = [ctypes.c_int]
+        lib.wsref_set_omp_threads.restype = None
+        lib.wsref_omp_threads.argtypes = []
+        lib.wsref_omp_threads.restype = ctypes.c_int
         _ref_lib = lib
     return _ref_lib
 
@@ -195,6 +199,24 @@ def oracle_tendencies(u, v, h, dx=1.0, dy=1.0, gravity=9.81, coriolis_f=0.0):
     getattr(lib, "wso_tendencies" + sfx)(W, H, dx, dy, gravity, coriolis_f, u.ctypes.data, v.ctypes.data,
                                          h.ctypes.data, du.ctypes.data, dv.ctypes.data, dh.ctypes.data)
     return du, dv, dh
+
+
+def oracle_omp_threads(n=None):
+    """Set (n > 0) and return the OpenMP team size of the C port."""
+    lib = _load_oracle()
+    lib.wso_set_omp_threads.argtypes = [ctypes.c_int]
+    lib.wso_omp_threads.restype = ctypes.c_int
+    if n:
+        lib.wso_set_omp_threads(int(n))
+    return int(lib.wso_omp_threads())
+
+
+def reference_omp_threads(n=None):
+    """Set (n > 0) and return the OpenMP team size of the reference build -- whatever OMP_NUM_THREADS said at load."""
+    lib = _load_ref()
+    if n:
+        lib.wsref_set_omp_threads(int(n))
+    return int(lib.wsref_omp_threads())
 
 
 class Reference(_SimBase):

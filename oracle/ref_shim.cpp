@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <unistd.h>
 #include <fcntl.h>
+#include <omp.h>
 
 using namespace weather_sim;
 
@@ -120,6 +121,19 @@ int wsref_apply_ic(void* s, const char* name) {
     sim->setInitialCondition(ic);
     sim->initialize();
     return 0;
+}
+
+// OpenMP team size the reference's `#pragma omp parallel for` (weather_simulation.cpp:503) really gets, and a
+// runtime override (launchers such as torchrun export OMP_NUM_THREADS=1 before this library is loaded).
+void wsref_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int wsref_omp_threads(void) {
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
 }
 
 }  // extern "C"

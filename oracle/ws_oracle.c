@@ -47,3 +47,22 @@ const char *wso_build_flags(void) {
     return "unknown";
 #endif
 }
+
+/* OpenMP team size of the port's one parallel loop, and a runtime override (launchers such as torchrun
+ * export OMP_NUM_THREADS=1 before this library is loaded). */
+#ifdef _OPENMP
+#include <omp.h>
+void wso_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int wso_omp_threads(void) {
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}
+#else
+void wso_set_omp_threads(int n) { (void)n; }
+int wso_omp_threads(void) { return 1; }
+#endif
