@@ -98,6 +98,15 @@ struct StepArgs {
     int y_begin, y_end;    // local OUTPUT row range this launch covers
     int y_begin2, y_end2;  // optional second range in the same launch (slab top + bottom edges); empty if equal
     int rows_per_chunk;    // rows each warp sweeps; 0 = library default
+    // Step overlap (single range, TMA kernel): consecutive steps are launched with programmatic stream serialization,
+    // so the CTAs of step n+1 fill the SMs while the last CTAs of step n drain. Data dependencies are tracked per
+    // chunk row instead of per kernel: every CTA bumps ovl_done[level * nchunks + chunk] when its rows are stored,
+    // and a CTA starts once the chunk rows c-1, c, c+1 of the PREVIOUS step have reached ovl_target x strips
+    // (ovl_target = protocol steps so far). ovl_done == nullptr: plain launch. ovl_chain: launch with the
+    // programmatic attribute.
+    unsigned *ovl_done;
+    unsigned ovl_target;
+    int ovl_chain;
 };
 
 // ---- kernel launchers (wsb_kernels.cu) -------------------------------------------------------
@@ -136,6 +145,7 @@ template <typename T>
 cudaError_t launch_step_tma(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
                             cudaStream_t st);
 bool step_tma_supported(int nstages, int dtype);
+int step_tma_rows_per_chunk();
 
 // rows [y0, y0+nrows) of a field from a dense float host block (nrows x W), replicated to every level and
 // converted to the grid's dtype (wsb_sim.cu; used by the blockwise initial conditions)

@@ -220,6 +220,11 @@ struct wsb_sim {
     HaloComm *comm = nullptr;
     double *d_partial = nullptr;
     int npartial = 0;
+    // step overlap (StepArgs::ovl_*): one counter per chunk row and level, protocol steps issued so far
+    unsigned *ovl_done = nullptr;
+    unsigned ovl_seq = 0;
+    bool ovl_enabled = false;
+    bool ovl_break = false;  // something other than a protocol step was enqueued last
 };
 
 static void *plane_origin(const wsb_sim *s, void *base) {
@@ -380,7 +385,7 @@ static StepArgs<T> step_args(const wsb_sim *s) {
 //   main stream                : wait previous ev_edge -> interior launch -> ev_interior
 // i.e. the edge bands and their exchange run beside the interior sweep instead of in front of it.
 template <typename T>
-static int enqueue_step_fused(wsb_sim *s) {
+static int enqueue_step_fused(wsb_sim *s, bool chain) {
     const Geometry<T> g = s->cur.geom<T>();
     const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
     StepArgs<T> a = step_args<T>(s);
@@ -388,6 +393,19 @@ static int enqueue_step_fused(wsb_sim *s) {
     const int halo = s->nstages;  // one ghost row per fused stage
     if (!s->comm) {
         a.y_begin = 0; a.y_end = H;
+        if (s->ovl_enabled) {
+            a.ovl_done = s->ovl_done;
+            a.ovl_target = s->ovl_seq;  // every chunk row has been bumped by all strips of ovl_seq earlier steps
+            a.ovl_chain = chain;        // only directly behind another protocol step on the stream
+            if (++s->ovl_seq >= (1u << 20)) {  // strips x steps must stay below 2^31: start over long before
+                WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
+                s->metrics.kernel_launches += 1;
+                WSB_CUDA(cudaMemsetAsync(s->ovl_done, 0, sizeof(unsigned) * s->cur.L * ((H + step_tma_rows_per_chunk() - 1) / step_tma_rows_per_chunk()), s->stream));
+                s->ovl_seq = 0;
+                s->ovl_break = true;  // the next launch follows a memset, not a step
+                return WSB_OK;
+            }
+        }
         WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
         s->metrics.kernel_launches += 1;
         return WSB_OK;
@@ -460,12 +478,16 @@ static int sim_ensure_halo(wsb_sim *s) {
     return WSB_OK;
 }
 
-// one step, enqueued (weather_simulation.cpp:117-158 without the host-side bookkeeping)
-static int sim_enqueue_step(wsb_sim *s) {
+// one step, enqueued (weather_simulation.cpp:117-158 without the host-side bookkeeping).
+// `follows_step`: the caller enqueued the previous step right before this one and nothing else in between -- the
+// only situation in which the step-overlap launch attribute is used.
+static int sim_enqueue_step(wsb_sim *s, bool follows_step = false) {
     WSB_TRY(sim_ensure_halo(s));
     if (is_step_path(s->path)) {
-        if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_fused<double>(s));
-        else WSB_TRY(enqueue_step_fused<float>(s));
+        const bool chain = follows_step && !s->ovl_break && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
+        s->ovl_break = false;
+        if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_fused<double>(s, chain));
+        else WSB_TRY(enqueue_step_fused<float>(s, chain));
     } else {
         if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_stages<double>(s));
         else WSB_TRY(enqueue_step_stages<float>(s));
@@ -855,6 +877,7 @@ static void sim_free(wsb_sim *s) {
     for (int k = 0; k < WSB_NUM_FIELDS; ++k)
         if (s->alt[k].base) cudaFree(s->alt[k].base);
     if (s->d_partial) cudaFree(s->d_partial);
+    if (s->ovl_done) cudaFree(s->ovl_done);
     grid_fini(&s->cur);
     cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior, s->ev_align};
     for (cudaEvent_t e : evs)
@@ -993,6 +1016,20 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             }
             if ((st = halo_comm_create(c.rank, c.nranks, c.nccl_unique_id, &s->comm)) != WSB_OK) break;
         }
+        // step overlap: single GPU, TMA whole-step kernel (WSB_STEP_OVERLAP=0 switches it off for A/B runs)
+        if (c.nranks == 1 && s->path == PATH_STEP_TMA) {
+            const char *e = std::getenv("WSB_STEP_OVERLAP");
+            s->ovl_enabled = !(e && std::atoi(e) == 0);
+            if (s->ovl_enabled) {
+                const int rpc = step_tma_rows_per_chunk();
+                const size_t n = (size_t)c.num_levels * ((s->nrows + rpc - 1) / rpc);
+                if (cudaMalloc(&s->ovl_done, n * sizeof(unsigned)) != cudaSuccess ||
+                    cudaMemsetAsync(s->ovl_done, 0, n * sizeof(unsigned), s->stream) != cudaSuccess) {
+                    st = cuda_fail(cudaGetLastError(), "cudaMalloc(step overlap counters)", __FILE__, __LINE__);
+                    break;
+                }
+            }
+        }
         s->npartial = 1024;
         if (cudaMalloc(&s->d_partial, sizeof(double) * 2 * s->npartial) != cudaSuccess) {
             st = cuda_fail(cudaGetLastError(), "cudaMalloc(partials)", __FILE__, __LINE__);
@@ -1032,7 +1069,7 @@ int wsb_sim_advance_async(wsb_sim *s, int32_t num_steps) {
     if (!s) return fail(WSB_ERR_INVALID_ARGUMENT, "sim is NULL");
     WSB_CUDA(cudaSetDevice(s->cur.device));
     WSB_TRY(sim_begin_timing(s, num_steps > 1));
-    for (int i = 0; i < num_steps; ++i) WSB_TRY(sim_enqueue_step(s));
+    for (int i = 0; i < num_steps; ++i) WSB_TRY(sim_enqueue_step(s, i > 0));
     return WSB_OK;
 }
 
@@ -1208,7 +1245,7 @@ int wsb_sim_run(wsb_sim *s, int32_t num_steps, int32_t *steps_done) {
     WSB_TRY(sim_begin_timing(s, num_steps > 1));
     int done = 0;
     for (int i = 0; i < num_steps; ++i) {
-        WSB_TRY(sim_enqueue_step(s));
+        WSB_TRY(sim_enqueue_step(s, i > 0));
         ++done;
         if (s->time >= s->cfg.max_time) break;  // :87-89, checked after the step
     }

@@ -71,6 +71,29 @@ __device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap *map,
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic <-> async proxy ordering for GLOBAL memory: rows stored by other CTAs (generic proxy), acquired through a
+// flag, are about to be read by the TMA engine (async proxy)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *p >= target (monotonic counter). A dependency that does not arrive within 5 s is a protocol bug: trap
+// instead of hanging the device.
+__device__ __forceinline__ void wait_counter(const unsigned *p, unsigned target) {
+    if ((int)(ld_acquire_gpu(p) - target) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_gpu(p) - target) < 0) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > 5000000000ull) __trap();
+    }
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <typename T, int V>
@@ -576,7 +599,25 @@ __global__ void __launch_bounds__(32, MINB)
     const int cy = second ? (int)blockIdx.y - nchunks1 : (int)blockIdx.y;
     const int y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
     const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
-    if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform
+    if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform (never taken when a.ovl_done is set: exact grid)
+    unsigned *ovl_slot = nullptr;
+    if (a.ovl_done) {
+        // step overlap (StepArgs): let the next step's grid start as soon as every CTA of this one is resident, and
+        // wait for the chunk rows of the previous step this CTA reads (c-1, c, c+1) and overwrites (c)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        unsigned *row = a.ovl_done + (size_t)blockIdx.z * gridDim.y;
+        ovl_slot = row + blockIdx.y;
+        if (a.ovl_target) {
+            if (lane == 0) {
+                const unsigned target = a.ovl_target * gridDim.x;  // every strip of a chunk row, every step so far
+                if (blockIdx.y > 0) wait_counter(ovl_slot - 1, target);
+                wait_counter(ovl_slot, target);
+                if (blockIdx.y + 1 < gridDim.y) wait_counter(ovl_slot + 1, target);
+            }
+            __syncwarp();
+            fence_proxy_async_global();
+        }
+    }
 
     SweepT<T, NST, V, RECIP, CL, FOLD> sw(g, ph, a);
     if constexpr (std::is_same<T, float>::value) {
@@ -625,14 +666,21 @@ __global__ void __launch_bounds__(32, MINB)
     __syncwarp();
     // RK4: CTAs away from every domain edge (the vast majority) run a loop body without any boundary handling
     // (0.578 -> 0.564 ms/step at 8192^2; no gain for the 1- and 2-stage kernels, which keep the single body)
-    if constexpr (NST == 4) {
-        const bool pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax;
-        if (pure) {
-            sw.template run<true>();
-            return;
+    bool pure = false;
+    if constexpr (NST == 4) pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax;
+    if (pure) {
+        if constexpr (NST == 4) sw.template run<true>();
+    } else {
+        sw.template run<false>();
+    }
+    if (ovl_slot) {  // this CTA's rows are stored: publish them to the next step's CTAs
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();  // release: cumulative over what the warp barrier made visible to this lane
+            atomicAdd(ovl_slot, 1u);
         }
     }
-    sw.template run<false>();
 }
 
 int env_int(const char *name, int dflt) {
@@ -692,24 +740,43 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     if (cudaError_t e = make_plane_map<T>(&tu, g, a.Y.u, L::SW)) return e;
     if (cudaError_t e = make_plane_map<T>(&tv, g, a.Y.v, L::SW)) return e;
     if (cudaError_t e = make_plane_map<T>(&th, g, a.Y.h, L::SW)) return e;
+    // step overlap needs ONE row range (the counters are indexed by blockIdx.y); ovl_chain adds the programmatic
+    // stream serialization attribute: this grid may start while the previous step's last CTAs still run
+    StepArgs<T> aa = a;
+    if (rows2 > 0) aa.ovl_done = nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(32, 1, 1);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = (aa.ovl_done && aa.ovl_chain) ? 1 : 0;
+    auto launch = [&](auto kernel, size_t smem) {
+        cfg.dynamicSmemBytes = smem;
+        return cudaLaunchKernelEx(&cfg, kernel, g, ph, aa, rpc, tu, tv, th);
+    };
     if constexpr (NST == 4) {
-        if (a.classical) {  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
-            if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, true, false><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
-            else step_tma_kernel<T, NST, V, false, MINB, true, false><<<grid, 32, L::smem_bytes(true), st>>>(g, ph, a, rpc, tu, tv, th);
-            return cudaGetLastError();
-        }
+        if (a.classical)  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
+            return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, true, false>, L::smem_bytes(true))
+                            : launch(step_tma_kernel<T, NST, V, false, MINB, true, false>, L::smem_bytes(true));
     }
     if constexpr (std::is_same<T, float>::value && V % 2 == 0) {
-        // folded arithmetic (opt-in): one spacing, exact reciprocal, coefficients that stay normal after scaling
-        if (a.fold && ph.recip && ph.rdx == ph.rdy) {
-            step_tma_kernel<T, NST, V, true, MINB, false, true><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
-            return cudaGetLastError();
-        }
+        // folded arithmetic (opt-in): one spacing, exact reciprocal
+        if (a.fold && ph.recip && ph.rdx == ph.rdy)
+            return launch(step_tma_kernel<T, NST, V, true, MINB, false, true>, L::smem_bytes(false));
     }
-    if (ph.recip) step_tma_kernel<T, NST, V, true, MINB, false, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
-    else step_tma_kernel<T, NST, V, false, MINB, false, false><<<grid, 32, L::smem_bytes(false), st>>>(g, ph, a, rpc, tu, tv, th);
-    return cudaGetLastError();
+    return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, false, false>, L::smem_bytes(false))
+                    : launch(step_tma_kernel<T, NST, V, false, MINB, false, false>, L::smem_bytes(false));
 }
+
+}  // namespace
+
+// rows per chunk of a full-height launch: the host sizes the step-overlap counters with it (one per chunk row)
+int step_tma_rows_per_chunk() { return rows_per_chunk_default(); }
+
+namespace {
 
 }  // namespace
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
-# Round-2 GPU session B: branch-free steady-state triple body A/B (lib/libweather_b200_nosteady.so = same sources
+# Round-2 GPU session B: step overlap (programmatic launch + chunk-row counters, WSB_STEP_OVERLAP=0/1) and
+# branch-free steady-state triple body A/B (lib/libweather_b200_nosteady.so = same sources
 # with -DWSB_STEADY_BODY=0), parity of the changed kernel, the full default bench line (other_configs, strong sub-line,
 # pybind leg) and the reference arm, ncu capture of the steady-body kernel.
 set -u
@@ -12,10 +13,15 @@ import sys,json
 d=json.loads(sys.stdin.read()); print('$1 %.4f ms/step %.2f Gcell/s frac %.3f clk %s' % (d['ms_per_step'], d['value']/1e9, d['roofline']['frac'], d['clocks']['sm_mhz']))"; }
 {
 for rep in 1 2 3; do
-  WSB_LIBRARY=$PWD/nvidia-jetson-workload_b200/lib/libweather_b200_nosteady.so $B --steps 100 --warmup 10 | line "rk4 strict nosteady rep$rep"
-  $B --steps 100 --warmup 10 | line "rk4 strict steady   rep$rep"
-  WSB_LIBRARY=$PWD/nvidia-jetson-workload_b200/lib/libweather_b200_nosteady.so $B --arith folded --steps 100 --warmup 10 | line "rk4 folded nosteady rep$rep"
-  $B --arith folded --steps 100 --warmup 10 | line "rk4 folded steady   rep$rep"
+  WSB_STEP_OVERLAP=0 WSB_LIBRARY=$PWD/nvidia-jetson-workload_b200/lib/libweather_b200_nosteady.so $B --steps 100 --warmup 10 | line "rk4 strict nosteady nooverlap rep$rep"
+  WSB_STEP_OVERLAP=0 $B --steps 100 --warmup 10 | line "rk4 strict steady   nooverlap rep$rep"
+  $B --steps 100 --warmup 10 | line "rk4 strict steady   overlap   rep$rep"
+  WSB_STEP_OVERLAP=0 $B --arith folded --steps 100 --warmup 10 | line "rk4 folded steady   nooverlap rep$rep"
+  $B --arith folded --steps 100 --warmup 10 | line "rk4 folded steady   overlap   rep$rep"
+done
+for w in swe8192_euler prim2048x64 baro16384_f64; do
+  WSB_STEP_OVERLAP=0 $B --workload $w --steps 50 --warmup 10 | line "$w nooverlap"
+  $B --workload $w --steps 50 --warmup 10 | line "$w overlap  "
 done
 for rpc in 40 52 64 76 88; do
   WSB_FUSED_ROWS_PER_CHUNK=$rpc $B --steps 50 --warmup 10 | line "rk4 strict steady rpc$rpc"
