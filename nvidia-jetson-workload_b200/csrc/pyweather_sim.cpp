@@ -9,8 +9,10 @@
 //   * SimulationConfig.double_precision is honoured (the reference ignores it): True selects
 //     the fp64 kernels and float64 arrays.
 //   * SimulationConfig.num_levels > 1 runs that many independent 2-D levels; arrays are (L, H, W).
-//   * SimulationConfig.rk4_classical / kernel_variant, WeatherSimulation.get_kernel_name(),
+//   * SimulationConfig.rk4_classical / kernel_variant / folded_arithmetic, WeatherSimulation.get_kernel_name(),
 //     WeatherSimulation.mass_energy(): B200-specific knobs and diagnostics.
+//   * SimulationConfig.rank / nranks / nccl_unique_id + pyweather_sim.nccl_unique_id(): row slabs over the GPUs of
+//     one box, one process per GPU; get_current_grid() is then this rank's slab (get_local_rows()).
 //   * OutputManager can be subclassed from Python (the reference binds the abstract base only).
 //   * get_current_grid() always views the CURRENT state (the reference's handle goes stale on odd steps).
 #include <pybind11/numpy.h>
@@ -82,6 +84,13 @@ struct SimulationConfig {  // weather_sim.hpp:155-191, same defaults
     // B200 additions
     bool rk4_classical = false;
     int kernel_variant = WSB_KERNEL_AUTO;
+    bool folded_arithmetic = false;  // wsb_arith_mode: WSB_ARITH_FOLDED (opt-in, see include/weather_b200.h)
+    // row-slab decomposition over the GPUs of one box (one process per GPU): this process is `rank` of `nranks`,
+    // grid_height is the GLOBAL height, nccl_unique_id the 128 bytes of pyweather_sim.nccl_unique_id() made on rank 0
+    // and handed to every rank (e.g. torch.distributed.broadcast_object_list / mpi4py bcast)
+    int rank = 0;
+    int nranks = 1;
+    std::string nccl_unique_id;
 };
 
 struct PerformanceMetrics {  // weather_sim.hpp:196-223
@@ -384,8 +393,15 @@ public:
         c.device_id = config.device_id;
         c.rk4_mode = config.rk4_classical ? WSB_RK4_CLASSICAL : WSB_RK4_REFERENCE;
         c.kernel_variant = config.kernel_variant;
-        c.rank = 0;
-        c.nranks = 1;
+        c.arith_mode = config.folded_arithmetic ? WSB_ARITH_FOLDED : WSB_ARITH_STRICT;
+        c.rank = config.rank;
+        c.nranks = config.nranks;
+        if (config.nranks > 1) {
+            if (config.nccl_unique_id.size() != WSB_NCCL_UNIQUE_ID_BYTES)
+                throw std::invalid_argument("SimulationConfig.nccl_unique_id must hold the 128 bytes of "
+                                            "pyweather_sim.nccl_unique_id() when nranks > 1");
+            c.nccl_unique_id = config.nccl_unique_id.data();
+        }
         check(wsb_sim_create(&c, &sim_));
         grid_.reset(new WeatherGrid(wsb_sim_current_grid(sim_)));
         // every backend of the reference maps onto the one B200 path (weather_simulation.cpp:562-591)
@@ -476,6 +492,11 @@ public:
         metrics_.reset();
     }
     std::string kernel_name() const { return wsb_sim_kernel_name(sim_); }
+    std::pair<int, int> local_rows() const {  // (row0, nrows) of the global grid this rank owns
+        int32_t r0 = 0, n = 0;
+        check(wsb_sim_local_rows(sim_, &r0, &n));
+        return {r0, n};
+    }
     std::pair<double, double> mass_energy() {
         double m = 0, e = 0;
         check(wsb_sim_mass_energy(sim_, &m, &e));
@@ -556,6 +577,11 @@ PYBIND11_MODULE(pyweather_sim, m) {
     m.doc() = "B200-native drop-in for the Weather Simulation workload's pyweather_sim module";
     m.attr("__backend__") = "libweather_b200 (sm_100a)";
     m.def("library_version", [] { return std::string(wsb_version()); });
+    m.def("nccl_unique_id", [] {
+        char id[WSB_NCCL_UNIQUE_ID_BYTES];
+        check(wsb_nccl_get_unique_id(id));
+        return py::bytes(id, sizeof(id));
+    }, "128-byte NCCL id for SimulationConfig.nccl_unique_id: make it on rank 0, hand the same bytes to every rank");
 
     py::enum_<SimulationModel>(m, "SimulationModel")
         .value("ShallowWater", SimulationModel::ShallowWater)
@@ -631,7 +657,13 @@ PYBIND11_MODULE(pyweather_sim, m) {
         .def_readwrite("output_path", &SimulationConfig::output_path)
         .def_readwrite("random_seed", &SimulationConfig::random_seed)
         .def_readwrite("rk4_classical", &SimulationConfig::rk4_classical)
-        .def_readwrite("kernel_variant", &SimulationConfig::kernel_variant);
+        .def_readwrite("kernel_variant", &SimulationConfig::kernel_variant)
+        .def_readwrite("folded_arithmetic", &SimulationConfig::folded_arithmetic)
+        .def_readwrite("rank", &SimulationConfig::rank)
+        .def_readwrite("nranks", &SimulationConfig::nranks)
+        .def_property(
+            "nccl_unique_id", [](const SimulationConfig &c) { return py::bytes(c.nccl_unique_id); },
+            [](SimulationConfig &c, const py::bytes &b) { c.nccl_unique_id = static_cast<std::string>(b); });
 
     py::class_<PerformanceMetrics>(m, "PerformanceMetrics")
         .def(py::init<>())
@@ -759,6 +791,7 @@ PYBIND11_MODULE(pyweather_sim, m) {
         .def("get_performance_metrics", &WeatherSimulation::metrics, py::return_value_policy::reference_internal)
         .def("reset_performance_metrics", &WeatherSimulation::reset_metrics)
         .def("get_kernel_name", &WeatherSimulation::kernel_name)
+        .def("get_local_rows", &WeatherSimulation::local_rows)
         .def("get_current_time_f64", &WeatherSimulation::current_time_f64)
         .def("mass_energy", &WeatherSimulation::mass_energy);
 

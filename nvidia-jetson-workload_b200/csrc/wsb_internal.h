@@ -105,6 +105,7 @@ struct StepArgs {
     // (ovl_target = protocol steps so far). ovl_done == nullptr: plain launch. ovl_chain: launch with the
     // programmatic attribute.
     unsigned *ovl_done;
+    unsigned *ovl_err;     // raised (mapped host memory) by a CTA whose dependency did not arrive in ~4 s
     unsigned ovl_target;
     int ovl_chain;
 };
@@ -162,8 +163,9 @@ int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out
 void halo_comm_destroy(HaloComm *c);
 int halo_align(HaloComm *c, cudaStream_t st);
 // Exchange `nrows` boundary rows of each of the `nplanes` planes with the up/down neighbours:
-// sends local rows [0,nrows) up and [H-nrows,H) down; receives into ghost rows [-nrows,0) and [H,H+nrows).
+// sends local rows [0,nrows) up and [H-nrows,H) down; receives into ghost rows [-nrows,0) and [H,H+nrows),
+// for each of the `levels` independent 2-D levels of every plane (one NCCL group for all of them).
 int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_size, int pitch, int H, int nrows,
-                  cudaStream_t st);
+                  int levels, long long level_stride, cudaStream_t st);
 
 }  // namespace wsb

@@ -137,14 +137,15 @@ int halo_align(HaloComm *c, cudaStream_t st) {
 }
 
 int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_size, int pitch, int H, int nrows,
-                  cudaStream_t st) {
+                  int levels, long long level_stride, cudaStream_t st) {
     const NcclApi *api = c->api;
     const size_t row_bytes = (size_t)pitch * elem_size;
     const size_t bytes = (size_t)nrows * row_bytes;
     const int up = c->rank - 1, down = c->rank + 1;
     WSB_NCCL(api, api->GroupStart());
+    for (int l = 0; l < levels; ++l)
     for (int k = 0; k < nplanes; ++k) {
-        char *o = (char *)planes[k];
+        char *o = (char *)planes[k] + (size_t)l * (size_t)level_stride * elem_size;
         if (up >= 0) {
             WSB_NCCL(api, api->Send(o, bytes, ncclInt8, up, c->comm, st));                                // my top rows
             WSB_NCCL(api, api->Recv(o - bytes, bytes, ncclInt8, up, c->comm, st));                        // ghosts above

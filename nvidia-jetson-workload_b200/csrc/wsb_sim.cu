@@ -223,6 +223,7 @@ struct wsb_sim {
     // step overlap (StepArgs::ovl_*): one counter per chunk row and level, protocol steps issued so far
     unsigned *ovl_done = nullptr;
     unsigned ovl_seq = 0;
+    unsigned *ovl_err = nullptr;  // mapped host word raised by a CTA whose dependency timed out
     bool ovl_enabled = false;
     bool ovl_break = false;  // something other than a protocol step was enqueued last
 };
@@ -274,8 +275,8 @@ static int sim_exchange(wsb_sim *s, void *const p[3], int nrows_halo, cudaEvent_
     WSB_CUDA(cudaStreamWaitEvent(s->comm_stream, after, 0));
     WSB_CUDA(cudaEventRecord(s->ev_h0, s->comm_stream));
     void *origins[3] = {plane_origin(s, p[0]), plane_origin(s, p[1]), plane_origin(s, p[2])};
-    WSB_TRY(halo_exchange(s->comm, origins, 3, elem_size(s->dtype), s->cur.pitch, s->cur.H, nrows_halo,
-                          s->comm_stream));
+    WSB_TRY(halo_exchange(s->comm, origins, 3, elem_size(s->dtype), s->cur.pitch, s->cur.H, nrows_halo, s->cur.L,
+                          s->cur.level_stride, s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_h1, s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
     return WSB_OK;
@@ -395,6 +396,7 @@ static int enqueue_step_fused(wsb_sim *s, bool chain) {
         a.y_begin = 0; a.y_end = H;
         if (s->ovl_enabled) {
             a.ovl_done = s->ovl_done;
+            a.ovl_err = s->ovl_err;
             a.ovl_target = s->ovl_seq;  // every chunk row has been bumped by all strips of ovl_seq earlier steps
             a.ovl_chain = chain;        // only directly behind another protocol step on the stream
             if (++s->ovl_seq >= (1u << 20)) {  // strips x steps must stay below 2^31: start over long before
@@ -537,6 +539,8 @@ static int sim_sync(wsb_sim *s) {
     if (s->edge_stream) WSB_CUDA(cudaStreamSynchronize(s->edge_stream));
     if (s->comm_stream) WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
     WSB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->ovl_err && *s->ovl_err)  // a step-overlap dependency that never arrived (protocol bug)
+        return fail(WSB_ERR_RUNTIME, "step overlap: a chunk-row dependency timed out; the state is invalid");
     if (s->run_open) {
         float ms = 0.f;
         WSB_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
@@ -878,6 +882,7 @@ static void sim_free(wsb_sim *s) {
         if (s->alt[k].base) cudaFree(s->alt[k].base);
     if (s->d_partial) cudaFree(s->d_partial);
     if (s->ovl_done) cudaFree(s->ovl_done);
+    if (s->ovl_err) cudaFreeHost(s->ovl_err);
     grid_fini(&s->cur);
     cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior, s->ev_align};
     for (cudaEvent_t e : evs)
@@ -916,8 +921,6 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         c.arith_mode = std::strcmp(e, "folded") == 0 ? WSB_ARITH_FOLDED : WSB_ARITH_STRICT;
     if (c.nranks < 1) c.nranks = 1;
     if (c.rank < 0 || c.rank >= c.nranks) return fail(WSB_ERR_INVALID_ARGUMENT, "rank out of range");
-    if (c.nranks > 1 && c.num_levels != 1)
-        return fail(WSB_ERR_INVALID_ARGUMENT, "row-slab decomposition supports num_levels == 1 only");
     if (c.nranks > 1 && !c.nccl_unique_id) return fail(WSB_ERR_INVALID_ARGUMENT, "nccl_unique_id is required when nranks > 1");
     if (c.nranks > c.grid_height) return fail(WSB_ERR_INVALID_ARGUMENT, "more ranks than grid rows");
 
@@ -1017,17 +1020,21 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             if ((st = halo_comm_create(c.rank, c.nranks, c.nccl_unique_id, &s->comm)) != WSB_OK) break;
         }
         // step overlap: single GPU, TMA whole-step kernel (WSB_STEP_OVERLAP=0 switches it off for A/B runs)
-        if (c.nranks == 1 && s->path == PATH_STEP_TMA) {
+        // (not for the Primitive model: its T/p pass sits between two steps, nothing to chain)
+        if (c.nranks == 1 && s->path == PATH_STEP_TMA && c.model != WSB_MODEL_PRIMITIVE_EQUATIONS) {
             const char *e = std::getenv("WSB_STEP_OVERLAP");
             s->ovl_enabled = !(e && std::atoi(e) == 0);
             if (s->ovl_enabled) {
                 const int rpc = step_tma_rows_per_chunk();
                 const size_t n = (size_t)c.num_levels * ((s->nrows + rpc - 1) / rpc);
+                // the error word lives in mapped host memory: the host reads it after a sync without any copy
                 if (cudaMalloc(&s->ovl_done, n * sizeof(unsigned)) != cudaSuccess ||
-                    cudaMemsetAsync(s->ovl_done, 0, n * sizeof(unsigned), s->stream) != cudaSuccess) {
+                    cudaMemsetAsync(s->ovl_done, 0, n * sizeof(unsigned), s->stream) != cudaSuccess ||
+                    cudaHostAlloc((void **)&s->ovl_err, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) {
                     st = cuda_fail(cudaGetLastError(), "cudaMalloc(step overlap counters)", __FILE__, __LINE__);
                     break;
                 }
+                *s->ovl_err = 0;
             }
         }
         s->npartial = 1024;
@@ -1325,7 +1332,8 @@ int wsb_sim_time_halo_exchange(wsb_sim *s, int32_t reps, double *us_per_exchange
     if (!s || !us_per_exchange) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
     *us_per_exchange = 0.0;
     const int depth = is_step_path(s->path) ? s->nstages : 1;
-    if (bytes_per_neighbour) *bytes_per_neighbour = (int64_t)depth * 3 * s->cur.pitch * (int64_t)elem_size(s->dtype);
+    if (bytes_per_neighbour)
+        *bytes_per_neighbour = (int64_t)depth * 3 * s->cur.L * s->cur.pitch * (int64_t)elem_size(s->dtype);
     if (!s->comm || reps <= 0) return WSB_OK;
     WSB_TRY(sim_sync(s));
     void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
@@ -1333,11 +1341,13 @@ int wsb_sim_time_halo_exchange(wsb_sim *s, int32_t reps, double *us_per_exchange
     const size_t es = elem_size(s->dtype);
     // the first exchanges absorb the skew between the ranks; the all-reduce pins the start of the timed ones
     for (int i = 0; i < 3; ++i)
-        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->comm_stream));
+        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->cur.L, s->cur.level_stride,
+                              s->comm_stream));
     WSB_TRY(halo_align(s->comm, s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_h0, s->comm_stream));
     for (int i = 0; i < reps; ++i)
-        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->comm_stream));
+        WSB_TRY(halo_exchange(s->comm, origins, 3, es, s->cur.pitch, s->cur.H, depth, s->cur.L, s->cur.level_stride,
+                              s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_h1, s->comm_stream));
     WSB_CUDA(cudaStreamSynchronize(s->comm_stream));
     float ms = 0.f;

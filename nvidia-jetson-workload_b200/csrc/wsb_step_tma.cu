@@ -74,26 +74,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // generic <-> async proxy ordering for GLOBAL memory: rows stored by other CTAs (generic proxy), acquired through a
 // flag, are about to be read by the TMA engine (async proxy)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// Spin until *p >= target (monotonic counter). A dependency that does not arrive within 5 s is a protocol bug: trap
-// instead of hanging the device.
-__device__ __forceinline__ void wait_counter(const unsigned *p, unsigned target) {
-    if ((int)(ld_acquire_gpu(p) - target) >= 0) return;
-    const unsigned long long t0 = global_timer_ns();
-    while ((int)(ld_acquire_gpu(p) - target) < 0) {
-        __nanosleep(64);
-        if (global_timer_ns() - t0 > 5000000000ull) __trap();
-    }
-}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <typename T, int V>
@@ -584,6 +570,41 @@ struct SweepT {
     }
 };
 
+// Step overlap (StepArgs::ovl_*). Written so that the warp provably never diverges: every lane polls the same
+// counters and the loop condition is a warp vote -- with a lane-0-only spin (or a call) in front of the sweep the
+// compiler can no longer prove convergence at the shuffles and emits a WARPSYNC.COLLECTIVE fallback for each of them
+// (twice the code, 6 % slower kernel).
+// enter: let the next step's grid start as soon as every CTA of this one is resident, then wait for the chunk rows of
+// the previous step this CTA reads (c-1, c, c+1) and overwrites (c). A dependency that has not arrived after ~4 s is
+// a protocol bug: the CTA gives up waiting and raises the error word (mapped host memory), which the host turns into
+// an error at the next synchronisation -- wrong numbers reported loudly instead of a hung device.
+__device__ __forceinline__ void overlap_enter(unsigned *done, unsigned steps_so_far, unsigned *err) {
+    if (!done) return;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!steps_so_far) return;
+    const unsigned *slot = done + (size_t)blockIdx.z * gridDim.y + blockIdx.y;
+    const unsigned target = steps_so_far * gridDim.x;  // every strip of a chunk row, every step so far
+    const unsigned *lo = blockIdx.y > 0 ? slot - 1 : slot, *hi = blockIdx.y + 1 < gridDim.y ? slot + 1 : slot;
+    unsigned tries = 0;
+    while (!__all_sync(kFull, (int)(ld_relaxed_gpu(lo) - target) >= 0 && (int)(ld_relaxed_gpu(slot) - target) >= 0 &&
+                                  (int)(ld_relaxed_gpu(hi) - target) >= 0)) {
+        __nanosleep(100);
+        if (++tries > 40000000u) {
+            if (err) *(volatile unsigned *)err = 1u;
+            break;
+        }
+    }
+    fence_acq_rel_gpu();         // acquire: the rows those CTAs stored before bumping their counters ...
+    fence_proxy_async_global();  // ... are read by the TMA engine (async proxy)
+}
+// leave: this CTA's rows are stored
+__device__ __forceinline__ void overlap_leave(unsigned *done) {
+    if (!done) return;
+    __syncwarp();
+    fence_acq_rel_gpu();  // release
+    if (threadIdx.x == 0) atomicAdd(done + (size_t)blockIdx.z * gridDim.y + blockIdx.y, 1u);
+}
+
 template <typename T, int NST, int V, bool RECIP, int MINB, bool CL, bool FOLD>
 __global__ void __launch_bounds__(32, MINB)
     step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk,
@@ -600,24 +621,7 @@ __global__ void __launch_bounds__(32, MINB)
     const int y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
     const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
     if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform (never taken when a.ovl_done is set: exact grid)
-    unsigned *ovl_slot = nullptr;
-    if (a.ovl_done) {
-        // step overlap (StepArgs): let the next step's grid start as soon as every CTA of this one is resident, and
-        // wait for the chunk rows of the previous step this CTA reads (c-1, c, c+1) and overwrites (c)
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        unsigned *row = a.ovl_done + (size_t)blockIdx.z * gridDim.y;
-        ovl_slot = row + blockIdx.y;
-        if (a.ovl_target) {
-            if (lane == 0) {
-                const unsigned target = a.ovl_target * gridDim.x;  // every strip of a chunk row, every step so far
-                if (blockIdx.y > 0) wait_counter(ovl_slot - 1, target);
-                wait_counter(ovl_slot, target);
-                if (blockIdx.y + 1 < gridDim.y) wait_counter(ovl_slot + 1, target);
-            }
-            __syncwarp();
-            fence_proxy_async_global();
-        }
-    }
+    overlap_enter(a.ovl_done, a.ovl_target, a.ovl_err);
 
     SweepT<T, NST, V, RECIP, CL, FOLD> sw(g, ph, a);
     if constexpr (std::is_same<T, float>::value) {
@@ -666,21 +670,18 @@ __global__ void __launch_bounds__(32, MINB)
     __syncwarp();
     // RK4: CTAs away from every domain edge (the vast majority) run a loop body without any boundary handling
     // (0.578 -> 0.564 ms/step at 8192^2; no gain for the 1- and 2-stage kernels, which keep the single body)
-    bool pure = false;
-    if constexpr (NST == 4) pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax;
-    if (pure) {
-        if constexpr (NST == 4) sw.template run<true>();
-    } else {
-        sw.template run<false>();
-    }
-    if (ovl_slot) {  // this CTA's rows are stored: publish them to the next step's CTAs
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();  // release: cumulative over what the warp barrier made visible to this lane
-            atomicAdd(ovl_slot, 1u);
+    // RK4: CTAs away from every domain edge (the vast majority) run a loop body without any boundary handling
+    // (0.578 -> 0.564 ms/step at 8192^2; no gain for the 1- and 2-stage kernels, which keep the single body)
+    if constexpr (NST == 4) {
+        const bool pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax;
+        if (pure) {
+            sw.template run<true>();
+            overlap_leave(a.ovl_done);  // this CTA's rows are stored: publish them to the next step's CTAs
+            return;
         }
     }
+    sw.template run<false>();
+    overlap_leave(a.ovl_done);
 }
 
 int env_int(const char *name, int dflt) {

@@ -102,6 +102,59 @@ def _worker(rank, world, port, cases, out_q):
                     ref = want[k] if not np.isnan(want[k]).all() else np.full((H, W), {"h": 10.0, "t": 288.15}.get(k, 0.0), np.float32)
                     if got[k].tobytes() != ref.tobytes():
                         msgs.append(f"slab initial condition {name} field {k} differs")
+        # Primitive model with independent levels on slabs: every level ≡ the 2-D oracle of that level, T/p drift included
+        W, H, Lv = 96, 50, 3
+        u, v, h = syn.white_noise_state(W, H, seed=5)
+        u3, v3, h3 = (np.stack([a * (1.0 + 0.25 * k) for k in range(Lv)]).astype(np.float32) for a in (u, v, h - 10.0))
+        h3 += 10.0
+        sim = wd.slab_simulation(W, H, rank, world, device_id=rank, model="primitive", integrator="rk2", num_levels=Lv,
+                                 coriolis_f=0.1, max_time=1e30)
+        r0, n = sim.local_rows
+        sim.set_state(u3[:, r0:r0 + n], v3[:, r0:r0 + n], h3[:, r0:r0 + n])
+        sim.step(3)
+        got = {k: wd.gather_rows(sim.get_field(k), 0) for k in ("u", "v", "h", "t", "p", "vorticity")}
+        sim.close()
+        if rank == 0:
+            for lev in range(Lv):
+                o = Oracle(W, H, 2, 1, coriolis_f=0.1)
+                o.set_state(u3[lev], v3[lev], h3[lev])
+                o.step(3)
+                for k in got:
+                    if got[k][lev].tobytes() != o.get_field(k).tobytes():
+                        msgs.append(f"primitive slabs level {lev} field {k} differs")
+                o.close()
+        # the drop-in surface on slabs: pyweather_sim.SimulationConfig.rank / nranks / nccl_unique_id
+        import weather_sim.pyweather_sim as m
+        W, H = 120, 90
+        u, v, h = syn.white_noise_state(W, H, seed=9)
+        c = m.SimulationConfig()
+        c.grid_width, c.grid_height = W, H
+        c.integration_method = m.IntegrationMethod.RungeKutta4
+        c.coriolis_f, c.max_time = 0.1, 1.0e9
+        c.device_id, c.rank, c.nranks = rank, rank, world
+        c.nccl_unique_id = wd.broadcast_bytes(m.nccl_unique_id() if rank == 0 else None, 0)
+        ps = m.WeatherSimulation(c)
+        ps.initialize()
+        r0, n = ps.get_local_rows()
+        g = ps.get_current_grid()
+        assert (g.get_height(), g.get_width()) == (n, W)
+        g.set_velocity_field(u[r0:r0 + n], v[r0:r0 + n])
+        g.set_height_field(h[r0:r0 + n])
+        ps.run(4)
+        ps.step()
+        pu, pv = ps.get_current_grid().get_velocity_field()
+        got = {"u": wd.gather_rows(pu, 0), "v": wd.gather_rows(pv, 0),
+               "h": wd.gather_rows(ps.get_current_grid().get_height_field(), 0),
+               "vorticity": wd.gather_rows(ps.get_current_grid().get_vorticity_field(), 0)}
+        del ps
+        if rank == 0:
+            o = Oracle(W, H, 0, 2, coriolis_f=float(np.float32(0.1)))
+            o.set_state(u, v, h)
+            o.step(5)
+            for k in got:
+                if got[k].tobytes() != o.get_field(k).tobytes():
+                    msgs.append(f"pyweather_sim on slabs: field {k} differs")
+            o.close()
         out_q.put(("ok" if not msgs else "; ".join(msgs), rank))
     except Exception as e:  # pragma: no cover
         import traceback
