@@ -63,7 +63,8 @@ struct Geometry {
 template <typename T>
 struct Physics {
     T ddx, ddy;    // 2.0f*dx, 2.0f*dy                         (used when !recip)
-    T rdx, rdy;    // exact reciprocals when both are powers of two (recip)
+    T rdx, rdy;    // recip: exact reciprocals (both spacings powers of two); else RN(1/ddx), RN(1/ddy) for the exact
+                   // three-operation division, or 0 = plain IEEE division (wsb_arith.cuh)
     T g, f;
     int recip;     // 1: (a-b)*rdx is bit-identical to (a-b)/ddx for every input
 };
@@ -146,7 +147,7 @@ template <typename T>
 cudaError_t launch_step_tma(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
                             cudaStream_t st);
 bool step_tma_supported(int nstages, int dtype);
-int step_tma_rows_per_chunk();
+int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L);
 
 // rows [y0, y0+nrows) of a field from a dense float host block (nrows x W), replicated to every level and
 // converted to the grid's dtype (wsb_sim.cu; used by the blockwise initial conditions)

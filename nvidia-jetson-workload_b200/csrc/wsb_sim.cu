@@ -8,7 +8,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,6 +55,45 @@ static bool is_pow2(double x) {
     return std::frexp(x, &e) == 0.5;
 }
 
+// Reciprocal for the three-operation division by a loop-invariant divisor (wsb_arith.cuh, div_by_invariant):
+// RN(1/d) if the sequence is PROVEN to return the correctly rounded quotient for this d, else 0 (= use the IEEE
+// division). fp32: proven by exhaustion -- inside the window the kernels apply it to, the sequence commutes with
+// scaling x by powers of two, so all 2^23 significands of one binade cover every operand (about 30 ms per divisor,
+// cached). fp64: by the theorem (Brisebarre, Muller, Raina 2004: correct for every x when r = RN(1/d), except
+// possibly for the all-ones significand of d, which is excluded).
+static double proven_reciprocal(double d, int dtype) {
+    if (std::getenv("WSB_IEEE_DIV")) return 0.0;
+    if (!(d >= 9.5367431640625e-07 && d <= 1048576.0)) return 0.0;  // 2^-20 .. 2^20: keeps q and the remainder normal
+    if (dtype == WSB_F64) {
+        unsigned long long bits;
+        std::memcpy(&bits, &d, sizeof(bits));
+        if ((bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull) return 0.0;
+        return 1.0 / d;
+    }
+    static std::mutex mu;
+    static std::map<float, float> cache;
+    const float df = (float)d;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(df);
+    if (it != cache.end()) return (double)it->second;
+    const volatile float rv = 1.0f / df;  // IEEE division in float: correctly rounded
+    const float r = rv;
+    bool ok = true;
+    for (uint32_t m = 0; m < (1u << 23) && ok; ++m) {
+        uint32_t b = 0x3F800000u | m;
+        float x;
+        std::memcpy(&x, &b, sizeof(x));
+        const volatile float q0 = x * r;  // volatile: one rounding each, nothing fused by the host compiler
+        const float q = q0;
+        const float e = std::fmaf(-q, df, x);
+        const float q1 = std::fmaf(e, r, q);
+        const volatile float want = x / df;
+        ok = q1 == want;
+    }
+    cache[df] = ok ? r : 0.0f;
+    return (double)cache[df];
+}
+
 }  // namespace wsb
 
 using namespace wsb;
@@ -70,6 +111,8 @@ struct wsb_grid {
     int dtype = WSB_F32;
     int device = 0;
     double dx = 1.0, dy = 1.0;   // already rounded to the grid dtype
+    double rdx = 0.5, rdy = 0.5; // reciprocals of 2dx, 2dy as the kernels use them (set_spacing_derived)
+    bool recip = true;
     int pitch = 0;               // elements
     long long level_stride = 0;  // elements
     int row0 = 0, Hglobal = 0;   // slab position (standalone grid: 0, H)
@@ -98,14 +141,29 @@ struct wsb_grid {
         const T tdx = (T)dx, tdy = (T)dy;
         p.ddx = T(2.0f) * tdx;  // `2.0f * dx` (weather_simulation.cpp:521): exact in both types
         p.ddy = T(2.0f) * tdy;
-        p.recip = is_pow2((double)p.ddx) && is_pow2((double)p.ddy);
-        p.rdx = p.recip ? T(1) / p.ddx : T(0);
-        p.rdy = p.recip ? T(1) / p.ddy : T(0);
+        p.recip = recip;
+        p.rdx = (T)rdx;
+        p.rdy = (T)rdy;
         p.g = (T)gravity;
         p.f = (T)coriolis;
         return p;
     }
 };
+
+// what the kernels need besides dx, dy: whether 2dx and 2dy are powers of two (then (a-b)/(2dx) IS the multiplication
+// by the exact reciprocal), else the proven reciprocals of the three-operation division (0 = IEEE division)
+static void set_spacing_derived(wsb_grid *g) {
+    const double ddx = 2.0 * g->dx, ddy = 2.0 * g->dy;  // exact: dx, dy are already values of the grid dtype
+    g->recip = is_pow2(ddx) && is_pow2(ddy);
+    if (g->recip) {
+        g->rdx = 1.0 / ddx;
+        g->rdy = 1.0 / ddy;
+    } else {
+        g->rdx = proven_reciprocal(ddx, g->dtype);
+        g->rdy = proven_reciprocal(ddy, g->dtype);
+        if (g->rdx == 0.0 || g->rdy == 0.0) g->rdx = g->rdy = 0.0;
+    }
+}
 
 static int grid_alloc_plane(wsb_grid *g, void **out) {
     WSB_CUDA(cudaSetDevice(g->device));
@@ -155,6 +213,7 @@ static int grid_init(wsb_grid *g, int W, int H, int L, double dx, double dy, int
     g->W = W; g->H = H; g->L = L; g->dtype = dtype; g->device = device;
     g->dx = dtype == WSB_F32 ? (double)(float)dx : dx;
     g->dy = dtype == WSB_F32 ? (double)(float)dy : dy;
+    set_spacing_derived(g);
     const int align = 128 / (int)elem_size(dtype);  // rows start on 128-byte boundaries
     g->pitch = (W + align - 1) / align * align;
     g->level_stride = (long long)(H + 2 * kLeadRows) * g->pitch;
@@ -223,6 +282,7 @@ struct wsb_sim {
     // step overlap (StepArgs::ovl_*): one counter per chunk row and level, protocol steps issued so far
     unsigned *ovl_done = nullptr;
     unsigned ovl_seq = 0;
+    int rpc = 64;  // rows per chunk of a full-height launch of the TMA whole-step kernel
     unsigned *ovl_err = nullptr;  // mapped host word raised by a CTA whose dependency timed out
     bool ovl_enabled = false;
     bool ovl_break = false;  // something other than a protocol step was enqueued last
@@ -376,6 +436,7 @@ static StepArgs<T> step_args(const wsb_sim *s) {
     a.dt6 = a.dt / T(6.0f);      // `dt_ / 6.0f` (:438)
     a.classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
     a.fold = s->cfg.arith_mode == WSB_ARITH_FOLDED;
+    a.rows_per_chunk = s->path == PATH_STEP_TMA ? s->rpc : 0;  // the register twin keeps its own default
     return a;
 }
 
@@ -402,7 +463,7 @@ static int enqueue_step_fused(wsb_sim *s, bool chain) {
             if (++s->ovl_seq >= (1u << 20)) {  // strips x steps must stay below 2^31: start over long before
                 WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
                 s->metrics.kernel_launches += 1;
-                WSB_CUDA(cudaMemsetAsync(s->ovl_done, 0, sizeof(unsigned) * s->cur.L * ((H + step_tma_rows_per_chunk() - 1) / step_tma_rows_per_chunk()), s->stream));
+                WSB_CUDA(cudaMemsetAsync(s->ovl_done, 0, sizeof(unsigned) * s->cur.L * ((H + s->rpc - 1) / s->rpc), s->stream));
                 s->ovl_seq = 0;
                 s->ovl_break = true;  // the next launch follows a memset, not a step
                 return WSB_OK;
@@ -717,6 +778,7 @@ int wsb_grid_set_spacing(wsb_grid *g, double dx, double dy) {
         return fail(WSB_ERR_INVALID_ARGUMENT, "Grid spacing must be positive");  // weather_grid.cpp:74-76
     g->dx = g->dtype == WSB_F32 ? (double)(float)dx : dx;
     g->dy = g->dtype == WSB_F32 ? (double)(float)dy : dy;
+    set_spacing_derived(g);
     return WSB_OK;
 }
 
@@ -1019,13 +1081,14 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             }
             if ((st = halo_comm_create(c.rank, c.nranks, c.nccl_unique_id, &s->comm)) != WSB_OK) break;
         }
+        s->rpc = step_tma_rows_per_chunk(s->nstages, s->dtype, c.grid_width, s->nrows, c.num_levels);
         // step overlap: single GPU, TMA whole-step kernel (WSB_STEP_OVERLAP=0 switches it off for A/B runs)
         // (not for the Primitive model: its T/p pass sits between two steps, nothing to chain)
         if (c.nranks == 1 && s->path == PATH_STEP_TMA && c.model != WSB_MODEL_PRIMITIVE_EQUATIONS) {
             const char *e = std::getenv("WSB_STEP_OVERLAP");
             s->ovl_enabled = !(e && std::atoi(e) == 0);
             if (s->ovl_enabled) {
-                const int rpc = step_tma_rows_per_chunk();
+                const int rpc = s->rpc;
                 const size_t n = (size_t)c.num_levels * ((s->nrows + rpc - 1) / rpc);
                 // the error word lives in mapped host memory: the host reads it after a sync without any copy
                 if (cudaMalloc(&s->ovl_done, n * sizeof(unsigned)) != cudaSuccess ||

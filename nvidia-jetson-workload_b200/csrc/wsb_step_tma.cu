@@ -23,6 +23,7 @@
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -689,11 +690,20 @@ int env_int(const char *name, int dflt) {
     return e ? std::atoi(e) : dflt;
 }
 
-int rows_per_chunk_default() {
-    // 64 rows + 8 pipeline-fill rows per warp: 12.5 % redundant sweep, ~19 k warps on 8192^2 (measured best
-    // among 32/64/96/128/192/256 on B200, profiles/r1/sweep_step_fused_tma.log)
-    static const int v = env_int("WSB_FUSED_ROWS_PER_CHUNK", 64);
-    return v > 0 ? v : 64;
+// Rows each warp sweeps. Every chunk pays 2*NST pipeline-fill iterations, so tall chunks win wherever the step
+// overlap hides the drain of the last CTAs (B200, 8192^2, profiles/r2/README.md): fp32 RK4 0.479 ms at 64 rows,
+// 0.456 at 160-192, 0.453 at 256; fp64 RK2 (16384^2) 2.23 / 2.09 / 2.11 ms at 64 / 128 / 192. The HBM-bound fp32
+// Euler kernel wants short chunks (0.257 / 0.260 / 0.282 / 0.313 ms at 64 / 88 / 128 / 192). Small grids get
+// shorter chunks so that there are at least about two CTAs per warp slot of the GPU.
+int rows_per_chunk_for(int nstages, bool f32, int W, int H, int L) {
+    static const int forced = env_int("WSB_FUSED_ROWS_PER_CHUNK", 0);
+    if (forced > 0) return forced;
+    const int cap = f32 ? (nstages == 4 ? 256 : 64) : (nstages == 2 ? 128 : 64);
+    const int cols = f32 ? (nstages == 2 ? 120 : 56) : (nstages == 4 ? 24 : 60);  // output columns per strip
+    const long long strips = (W + cols - 1) / cols;
+    long long rpc = strips * (long long)H * L / (2 * 148 * 16);
+    rpc = (rpc + 15) / 16 * 16;
+    return (int)std::max<long long>(32, std::min<long long>(cap, rpc));
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
@@ -734,7 +744,8 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     const int rows = a.y_end - a.y_begin, rows2 = a.y_end2 - a.y_begin2;
     if (rows <= 0) return cudaSuccess;
     const int strips = (g.W + L::OUTW - 1) / L::OUTW;
-    const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk : rows_per_chunk_default();
+    const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk
+                                         : rows_per_chunk_for(NST, std::is_same<T, float>::value, g.W, g.H, g.L);
     const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
     const dim3 grid(strips, chunks, g.L);
     CUtensorMap tu, tv, th;
@@ -775,7 +786,9 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
 }  // namespace
 
 // rows per chunk of a full-height launch: the host sizes the step-overlap counters with it (one per chunk row)
-int step_tma_rows_per_chunk() { return rows_per_chunk_default(); }
+int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L) {
+    return rows_per_chunk_for(nstages, dtype == WSB_F32, W, H, L);
+}
 
 namespace {
 
