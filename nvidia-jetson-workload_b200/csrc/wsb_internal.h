@@ -88,6 +88,21 @@ struct StageArgs {
     int y_begin, y_end;   // local row range this launch covers
 };
 
+// Fused ghost exchange over peer memory (row slabs, TMA whole-step kernel): ONE launch per step and rank. The chunk
+// rows are laid out as [top band | bottom band | interior chunks]; the CTAs of a band wait for the neighbour's flag
+// before they read the ghost rows, store their output rows BOTH locally and -- through an NVLink peer mapping of the
+// neighbour's planes (cudaIpc) -- into the neighbour's ghost rows, and bump the neighbour's flag. No NCCL kernel, no
+// edge launch and no stream event is left in a step; the transfer rides under the interior sweep.
+template <typename T>
+struct PeerExchange {
+    int band;                   // ghost depth (rows per band); 0 = exchange not fused into this launch
+    Planes3<T> up, dn;          // the neighbours' y_{n+1} planes (origin pointers in THIS process), null at domain ends
+    int up_H, dn_H;             // their local row counts (level stride and ghost-row position over there)
+    unsigned *wait;             // local flags: [0] bumped by the upper neighbour's bottom band, [1] by the lower one's top
+    unsigned *sig_up, *sig_dn;  // the flags to bump over there: up's [1], dn's [0]
+    unsigned target;            // fused steps so far (flags count strips x levels per step)
+};
+
 // Whole-step fused kernel arguments (all RK stages in one pass over the grid).
 template <typename T>
 struct StepArgs {
@@ -105,6 +120,7 @@ struct StepArgs {
     // and a CTA starts once the chunk rows c-1, c, c+1 of the PREVIOUS step have reached ovl_target x strips
     // (ovl_target = protocol steps so far). ovl_done == nullptr: plain launch. ovl_chain: launch with the
     // programmatic attribute.
+    PeerExchange<T> px;
     unsigned *ovl_done;
     unsigned *ovl_err;     // raised (mapped host memory) by a CTA whose dependency did not arrive in ~4 s
     unsigned ovl_target;
@@ -147,7 +163,8 @@ template <typename T>
 cudaError_t launch_step_tma(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, int nstages,
                             cudaStream_t st);
 bool step_tma_supported(int nstages, int dtype);
-int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L);
+int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L, bool overlapped);
+int step_tma_strips(int nstages, int dtype, int W);
 
 // rows [y0, y0+nrows) of a field from a dense float host block (nrows x W), replicated to every level and
 // converted to the grid's dtype (wsb_sim.cu; used by the blockwise initial conditions)
@@ -163,6 +180,20 @@ struct HaloComm;  // opaque: communicator + neighbour ranks
 int halo_comm_create(int rank, int nranks, const void *unique_id, HaloComm **out);
 void halo_comm_destroy(HaloComm *c);
 int halo_align(HaloComm *c, cudaStream_t st);
+// Peer mappings of one neighbour's memory for the fused ghost exchange: [0..2] u, v, h of plane set A, [3..5] of plane
+// set B, [6] its two flag words.
+constexpr int kPeerPointers = 7;
+struct PeerLink {
+    void *mapped[kPeerPointers] = {};  // allocation bases as mapped here
+    bool owned[kPeerPointers] = {};    // this entry opened the mapping (several pointers may share an allocation)
+    void *ptr[kPeerPointers] = {};     // the neighbour's pointers, usable in this process
+    int H = 0;                         // its local row count
+    bool present = false;
+};
+// Collective over all ranks of the communicator. *all_ok: every rank mapped every neighbour (else nothing is mapped).
+int peer_setup(HaloComm *c, void *const local[kPeerPointers], int H, PeerLink *up, PeerLink *dn, bool *all_ok,
+               cudaStream_t st);
+void peer_close(PeerLink *link);
 // Exchange `nrows` boundary rows of each of the `nplanes` planes with the up/down neighbours:
 // sends local rows [0,nrows) up and [H-nrows,H) down; receives into ghost rows [-nrows,0) and [H,H+nrows),
 // for each of the `levels` independent 2-D levels of every plane (one NCCL group for all of them).

@@ -6,6 +6,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -156,6 +158,126 @@ int halo_exchange(HaloComm *c, void *const *planes, int nplanes, size_t elem_siz
         }
     }
     WSB_NCCL(api, api->GroupEnd());
+    return WSB_OK;
+}
+
+// ---- peer mappings for the fused ghost exchange (PeerExchange, wsb_internal.h) ---------------------------------
+// Each rank exports its six state planes (both buffers of u, v, h) and its flag words with cudaIpcGetMemHandle and
+// hands the handles to its two neighbours through the NCCL communicator it already has (one ncclSend/ncclRecv group
+// of 592-byte blobs); the neighbours map them with cudaIpcOpenMemHandle. cudaMalloc may carve several small planes
+// out of one allocation, and an IPC handle always names the WHOLE allocation, so every pointer travels as
+// (handle, offset from the allocation base). All ranks then agree (all-reduce) whether every mapping succeeded:
+// the fused exchange is used by all ranks or by none.
+namespace {
+struct PeerBlob {
+    cudaIpcMemHandle_t handle[kPeerPointers];
+    unsigned long long offset[kPeerPointers];
+    int H;
+    int valid;
+};
+
+using MemGetAddressRangeFn = int (*)(unsigned long long *, size_t *, unsigned long long);
+MemGetAddressRangeFn address_range_fn() {
+    static MemGetAddressRangeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<MemGetAddressRangeFn>(p);
+    }();
+    return fn;
+}
+
+bool open_link(const PeerBlob &b, PeerLink *link) {
+    if (!b.valid) return false;
+    link->H = b.H;
+    for (int k = 0; k < kPeerPointers; ++k) {
+        // the same allocation may back several pointers: map it once
+        void *base = nullptr;
+        for (int j = 0; j < k; ++j)
+            if (std::memcmp(&b.handle[j], &b.handle[k], sizeof(cudaIpcMemHandle_t)) == 0) base = link->mapped[j];
+        if (!base) {
+            if (cudaIpcOpenMemHandle(&base, b.handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            link->owned[k] = true;
+        }
+        link->mapped[k] = base;
+        link->ptr[k] = (char *)base + b.offset[k];
+    }
+    link->present = true;
+    return true;
+}
+}  // namespace
+
+void peer_close(PeerLink *link) {
+    for (int k = 0; k < kPeerPointers; ++k) {
+        if (link->owned[k] && link->mapped[k]) cudaIpcCloseMemHandle(link->mapped[k]);
+        link->owned[k] = false;
+        link->mapped[k] = link->ptr[k] = nullptr;
+    }
+    link->present = false;
+}
+
+int peer_setup(HaloComm *c, void *const local[kPeerPointers], int H, PeerLink *up, PeerLink *dn, bool *all_ok,
+               cudaStream_t st) {
+    const NcclApi *api = c->api;
+    *all_ok = false;
+    PeerBlob mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.H = H;
+    mine.valid = std::getenv("WSB_NO_PEER_EXCHANGE") ? 0 : 1;
+    MemGetAddressRangeFn range = address_range_fn();
+    if (!range) mine.valid = 0;
+    for (int k = 0; k < kPeerPointers && mine.valid; ++k) {
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (range(&base, &size, (unsigned long long)(uintptr_t)local[k]) != 0 ||
+            cudaIpcGetMemHandle(&mine.handle[k], (void *)(uintptr_t)base) != cudaSuccess) {
+            cudaGetLastError();
+            mine.valid = 0;
+            break;
+        }
+        mine.offset[k] = (unsigned long long)(uintptr_t)local[k] - base;
+    }
+    // blobs travel through device staging buffers: [0] mine, [1] from up, [2] from down
+    PeerBlob *dev = nullptr;
+    WSB_CUDA(cudaMalloc(&dev, 3 * sizeof(PeerBlob)));
+    WSB_CUDA(cudaMemsetAsync(dev, 0, 3 * sizeof(PeerBlob), st));
+    WSB_CUDA(cudaMemcpyAsync(dev, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    const int r_up = c->rank - 1, r_dn = c->rank + 1;
+    WSB_NCCL(api, api->GroupStart());
+    if (r_up >= 0) {
+        WSB_NCCL(api, api->Send(dev, sizeof(PeerBlob), ncclInt8, r_up, c->comm, st));
+        WSB_NCCL(api, api->Recv(dev + 1, sizeof(PeerBlob), ncclInt8, r_up, c->comm, st));
+    }
+    if (r_dn < c->nranks) {
+        WSB_NCCL(api, api->Send(dev, sizeof(PeerBlob), ncclInt8, r_dn, c->comm, st));
+        WSB_NCCL(api, api->Recv(dev + 2, sizeof(PeerBlob), ncclInt8, r_dn, c->comm, st));
+    }
+    WSB_NCCL(api, api->GroupEnd());
+    PeerBlob got[2];
+    WSB_CUDA(cudaMemcpyAsync(got, dev + 1, 2 * sizeof(PeerBlob), cudaMemcpyDeviceToHost, st));
+    WSB_CUDA(cudaStreamSynchronize(st));
+    bool ok = mine.valid != 0;
+    if (ok && r_up >= 0) ok = open_link(got[0], up);
+    if (ok && r_dn < c->nranks) ok = open_link(got[1], dn);
+    // every rank uses the fused exchange, or none does
+    const float flag = ok ? 1.0f : 0.0f;
+    float agreed = 0.0f;
+    WSB_CUDA(cudaMemcpyAsync(c->scratch, &flag, sizeof(flag), cudaMemcpyHostToDevice, st));
+    WSB_NCCL(api, api->AllReduce(c->scratch, c->scratch, 1, ncclFloat, ncclMin, c->comm, st));
+    WSB_CUDA(cudaMemcpyAsync(&agreed, c->scratch, sizeof(agreed), cudaMemcpyDeviceToHost, st));
+    WSB_CUDA(cudaMemsetAsync(c->scratch, 0, sizeof(float), st));
+    WSB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dev);
+    *all_ok = agreed > 0.5f;
+    if (!*all_ok) {
+        peer_close(up);
+        peer_close(dn);
+    }
     return WSB_OK;
 }
 

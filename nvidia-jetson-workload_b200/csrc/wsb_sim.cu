@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "wsb_internal.h"
@@ -277,6 +278,16 @@ struct wsb_sim {
     double last_run_ms = 0.0;
     wsb_metrics metrics{};
     HaloComm *comm = nullptr;
+    // fused ghost exchange over peer memory (PeerExchange, wsb_internal.h): all ranks or none
+    bool peer_ok = false;
+    PeerLink peer_up, peer_dn;
+    unsigned *xflags = nullptr;     // [0] bumped by the upper neighbour, [1] by the lower one
+    unsigned x_seq = 0;             // fused steps so far
+    int band_ctas = 0;              // CTAs per band and step (strips x levels): what one step adds to a flag
+    void *setA[3] = {}, *setB[3] = {};  // the two plane sets as they were when the neighbours mapped them
+    bool ghosts_in_flight = false;  // the ghost rows of the current state are being pushed by the neighbours' last
+                                    // step: kernels that wait on the flags may use them, host-ordered consumers not yet
+    bool nccl_ghosts_pending = false;  // an NCCL exchange was enqueued that the main stream has not waited for
     double *d_partial = nullptr;
     int npartial = 0;
     // step overlap (StepArgs::ovl_*): one counter per chunk row and level, protocol steps issued so far
@@ -339,6 +350,7 @@ static int sim_exchange(wsb_sim *s, void *const p[3], int nrows_halo, cudaEvent_
                           s->cur.level_stride, s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_h1, s->comm_stream));
     WSB_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+    s->nccl_ghosts_pending = true;
     return WSB_OK;
 }
 
@@ -460,17 +472,50 @@ static int enqueue_step_fused(wsb_sim *s, bool chain) {
             a.ovl_err = s->ovl_err;
             a.ovl_target = s->ovl_seq;  // every chunk row has been bumped by all strips of ovl_seq earlier steps
             a.ovl_chain = chain;        // only directly behind another protocol step on the stream
-            if (++s->ovl_seq >= (1u << 20)) {  // strips x steps must stay below 2^31: start over long before
-                WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
-                s->metrics.kernel_launches += 1;
-                WSB_CUDA(cudaMemsetAsync(s->ovl_done, 0, sizeof(unsigned) * s->cur.L * ((H + s->rpc - 1) / s->rpc), s->stream));
-                s->ovl_seq = 0;
-                s->ovl_break = true;  // the next launch follows a memset, not a step
-                return WSB_OK;
-            }
+            ++s->ovl_seq;               // (counters and targets wrap together: the kernel compares differences)
         }
         WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
         s->metrics.kernel_launches += 1;
+        return WSB_OK;
+    }
+    if (s->peer_ok) {
+        // fused ghost exchange: ONE launch; the band CTAs wait for, push to and signal the neighbours themselves
+        const int which = s->next[0] == s->setB[0] ? 1 : s->next[0] == s->setA[0] ? 0 : -1;
+        if (which < 0) return fail(WSB_ERR_RUNTIME, "fused ghost exchange: the state planes are not the mapped ones");
+        const size_t lead = (size_t)kLeadRows * s->cur.pitch * sizeof(T);
+        auto peer_planes = [&](const PeerLink &l) {
+            Planes3<T> p;
+            p.u = l.present ? (T *)((char *)l.ptr[which * 3 + 0] + lead) : nullptr;
+            p.v = l.present ? (T *)((char *)l.ptr[which * 3 + 1] + lead) : nullptr;
+            p.h = l.present ? (T *)((char *)l.ptr[which * 3 + 2] + lead) : nullptr;
+            return p;
+        };
+        a.y_begin = 0; a.y_end = H;
+        a.px.band = halo;
+        a.px.up = peer_planes(s->peer_up);
+        a.px.dn = peer_planes(s->peer_dn);
+        a.px.up_H = s->peer_up.H;
+        a.px.dn_H = s->peer_dn.H;
+        a.px.wait = s->xflags;
+        a.px.sig_up = s->peer_up.present ? (unsigned *)s->peer_up.ptr[6] + 1 : nullptr;
+        a.px.sig_dn = s->peer_dn.present ? (unsigned *)s->peer_dn.ptr[6] + 0 : nullptr;
+        a.px.target = s->x_seq;
+        a.ovl_err = s->ovl_err;
+        if (s->ovl_enabled) {
+            a.ovl_done = s->ovl_done;
+            a.ovl_target = s->ovl_seq;
+            a.ovl_chain = chain && !s->nccl_ghosts_pending;
+            ++s->ovl_seq;
+        }
+        if (s->nccl_ghosts_pending) {  // ghost rows that came through NCCL (first step after an upload)
+            WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+            s->nccl_ghosts_pending = false;
+        }
+        WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
+        s->metrics.kernel_launches += 1;
+        ++s->x_seq;
+        s->band_ctas = step_tma_strips(s->nstages, s->dtype, s->cur.W) * s->cur.L;
+        s->ghosts_in_flight = true;
         return WSB_OK;
     }
     static const bool no_exchange = [] {  // timing diagnostics ONLY: results are wrong next to the slab seams
@@ -530,7 +575,15 @@ static int enqueue_primitive_tp(wsb_sim *s) {
     return WSB_OK;
 }
 
-static int sim_ensure_halo(wsb_sim *s) {
+// `flag_aware`: the consumer is a fused-exchange step, whose band CTAs wait for the neighbours' flags themselves.
+// Anything else (diagnostics, a rendezvous) needs the ghost rows to be complete in stream order: if the last steps
+// delivered them by peer stores, they are exchanged once more through NCCL (same values; a late peer store into the
+// same rows is harmless).
+static int sim_ensure_halo(wsb_sim *s, bool flag_aware = false) {
+    if (s->comm && s->ghosts_in_flight && !flag_aware) {
+        s->ghosts_in_flight = false;
+        s->halo_valid = false;
+    }
     if (!s->comm || s->halo_valid) return WSB_OK;
     void *cur3[3] = {s->cur.f[0].base, s->cur.f[1].base, s->cur.f[2].base};
     WSB_CUDA(cudaEventRecord(s->ev_edge, s->stream));      // "the current state is complete" for the comm stream
@@ -545,7 +598,7 @@ static int sim_ensure_halo(wsb_sim *s) {
 // `follows_step`: the caller enqueued the previous step right before this one and nothing else in between -- the
 // only situation in which the step-overlap launch attribute is used.
 static int sim_enqueue_step(wsb_sim *s, bool follows_step = false) {
-    WSB_TRY(sim_ensure_halo(s));
+    WSB_TRY(sim_ensure_halo(s, s->peer_ok && is_step_path(s->path)));
     if (is_step_path(s->path)) {
         const bool chain = follows_step && !s->ovl_break && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
         s->ovl_break = false;
@@ -577,7 +630,7 @@ static int sim_enqueue_step(wsb_sim *s, bool follows_step = false) {
 static int sim_begin_timing(wsb_sim *s, bool align = false) {
     if (!s->run_open) {
         if (align && s->comm) {
-            WSB_TRY(sim_ensure_halo(s));
+            WSB_TRY(sim_ensure_halo(s, s->peer_ok));
             WSB_CUDA(cudaEventRecord(s->ev_align, s->stream));
             WSB_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_align, 0));
             WSB_TRY(halo_align(s->comm, s->comm_stream));
@@ -912,8 +965,11 @@ int wsb_grid_swap(wsb_grid *a, wsb_grid *b) {
     WSB_CUDA(cudaStreamSynchronize(a->stream));
     WSB_CUDA(cudaStreamSynchronize(b->stream));
     for (int k = 0; k < WSB_NUM_FIELDS; ++k) std::swap(a->f[k], b->f[k]);
-    if (a->owner) a->owner->halo_valid = false;
-    if (b->owner) b->owner->halo_valid = false;
+    for (wsb_grid *g : {a, b})
+        if (g->owner) {
+            g->owner->halo_valid = false;
+            g->owner->ghosts_in_flight = false;
+        }
     return WSB_OK;
 }
 
@@ -938,6 +994,23 @@ static void sim_free(wsb_sim *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     if (s->edge_stream) cudaStreamSynchronize(s->edge_stream);
+    if (s->comm && s->peer_ok) {
+        // The neighbours store into this rank's ghost rows. For every fused step this rank has run, each neighbour
+        // runs the same step (SPMD) and bumps this rank's flag once per band CTA AFTER its stores: wait (bounded)
+        // until both flags have seen all x_seq steps, i.e. no store into this memory is in flight or still to come.
+        const unsigned want = s->x_seq * (unsigned)s->band_ctas;
+        for (int tries = 0; tries < 5000; ++tries) {
+            unsigned f[2] = {want, want};
+            if (cudaMemcpy(f, s->xflags, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+            const bool up_done = !s->peer_up.present || (int)(f[0] - want) >= 0;
+            const bool dn_done = !s->peer_dn.present || (int)(f[1] - want) >= 0;
+            if (up_done && dn_done) break;
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        peer_close(&s->peer_up);
+        peer_close(&s->peer_dn);
+    }
+    if (s->xflags) cudaFree(s->xflags);
     if (s->comm) halo_comm_destroy(s->comm);
     sim_free3(s->next); sim_free3(s->tA); sim_free3(s->tB); sim_free3(s->k1); sim_free3(s->k2); sim_free3(s->k3);
     for (int k = 0; k < WSB_NUM_FIELDS; ++k)
@@ -1081,24 +1154,46 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
             }
             if ((st = halo_comm_create(c.rank, c.nranks, c.nccl_unique_id, &s->comm)) != WSB_OK) break;
         }
-        s->rpc = step_tma_rows_per_chunk(s->nstages, s->dtype, c.grid_width, s->nrows, c.num_levels);
-        // step overlap: single GPU, TMA whole-step kernel (WSB_STEP_OVERLAP=0 switches it off for A/B runs)
-        // (not for the Primitive model: its T/p pass sits between two steps, nothing to chain)
-        if (c.nranks == 1 && s->path == PATH_STEP_TMA && c.model != WSB_MODEL_PRIMITIVE_EQUATIONS) {
-            const char *e = std::getenv("WSB_STEP_OVERLAP");
-            s->ovl_enabled = !(e && std::atoi(e) == 0);
-            if (s->ovl_enabled) {
-                const int rpc = s->rpc;
-                const size_t n = (size_t)c.num_levels * ((s->nrows + rpc - 1) / rpc);
-                // the error word lives in mapped host memory: the host reads it after a sync without any copy
-                if (cudaMalloc(&s->ovl_done, n * sizeof(unsigned)) != cudaSuccess ||
-                    cudaMemsetAsync(s->ovl_done, 0, n * sizeof(unsigned), s->stream) != cudaSuccess ||
-                    cudaHostAlloc((void **)&s->ovl_err, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) {
-                    st = cuda_fail(cudaGetLastError(), "cudaMalloc(step overlap counters)", __FILE__, __LINE__);
-                    break;
-                }
-                *s->ovl_err = 0;
+        // fused ghost exchange over peer memory: TMA whole-step kernel, slabs at least three ghost bands deep (tested
+        // on the smallest slab of the partition so that every rank decides alike), every neighbour mappable
+        if (c.nranks > 1 && s->path == PATH_STEP_TMA && c.grid_height / c.nranks >= 3 * s->nstages) {
+            if (cudaMalloc(&s->xflags, 2 * sizeof(unsigned)) != cudaSuccess ||
+                cudaMemsetAsync(s->xflags, 0, 2 * sizeof(unsigned), s->stream) != cudaSuccess) {
+                st = cuda_fail(cudaGetLastError(), "cudaMalloc(exchange flags)", __FILE__, __LINE__);
+                break;
             }
+            for (int k = 0; k < 3; ++k) {
+                s->setA[k] = s->cur.f[k].base;
+                s->setB[k] = s->next[k];
+            }
+            void *local[kPeerPointers] = {s->setA[0], s->setA[1], s->setA[2], s->setB[0], s->setB[1], s->setB[2], s->xflags};
+            if (cudaStreamSynchronize(s->stream) != cudaSuccess) {
+                st = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
+                break;
+            }
+            if ((st = peer_setup(s->comm, local, s->nrows, &s->peer_up, &s->peer_dn, &s->peer_ok, s->comm_stream)) != WSB_OK) break;
+        }
+        // step overlap: TMA whole-step kernel, one launch per step (single GPU, or slabs with the fused exchange);
+        // not for the Primitive model (its T/p pass sits between two steps). WSB_STEP_OVERLAP=0 switches it off.
+        const bool one_launch = s->path == PATH_STEP_TMA && (c.nranks == 1 || s->peer_ok);
+        {
+            const char *e = std::getenv("WSB_STEP_OVERLAP");
+            s->ovl_enabled = one_launch && c.model != WSB_MODEL_PRIMITIVE_EQUATIONS && !(e && std::atoi(e) == 0);
+        }
+        s->rpc = step_tma_rows_per_chunk(s->nstages, s->dtype, c.grid_width, s->nrows, c.num_levels, s->ovl_enabled);
+        if (one_launch) {
+            // one counter per chunk row and level; with the fused exchange the chunk rows are [bands | interior chunks]
+            const int chunk_rows = s->peer_ok ? 2 + (s->nrows - 2 * s->nstages + s->rpc - 1) / s->rpc
+                                              : (s->nrows + s->rpc - 1) / s->rpc;
+            const size_t n = (size_t)c.num_levels * chunk_rows;
+            // the error word lives in mapped host memory: the host reads it after a sync without any copy
+            if ((s->ovl_enabled && (cudaMalloc(&s->ovl_done, n * sizeof(unsigned)) != cudaSuccess ||
+                                    cudaMemsetAsync(s->ovl_done, 0, n * sizeof(unsigned), s->stream) != cudaSuccess)) ||
+                cudaHostAlloc((void **)&s->ovl_err, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) {
+                st = cuda_fail(cudaGetLastError(), "cudaMalloc(step overlap counters)", __FILE__, __LINE__);
+                break;
+            }
+            *s->ovl_err = 0;
         }
         s->npartial = 1024;
         if (cudaMalloc(&s->d_partial, sizeof(double) * 2 * s->npartial) != cudaSuccess) {
@@ -1416,7 +1511,8 @@ int wsb_sim_time_halo_exchange(wsb_sim *s, int32_t reps, double *us_per_exchange
     float ms = 0.f;
     WSB_CUDA(cudaEventElapsedTime(&ms, s->ev_h0, s->ev_h1));
     *us_per_exchange = 1.0e3 * ms / reps;
-    s->halo_valid = true;  // exchanging the current state is idempotent
+    s->halo_valid = false;  // (the next step re-establishes the ghost rows in its own stream order)
+    s->ghosts_in_flight = false;
     return WSB_OK;
 }
 

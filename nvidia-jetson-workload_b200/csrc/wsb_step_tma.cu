@@ -81,6 +81,12 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <typename T, int V>
@@ -141,7 +147,8 @@ struct Layout {
     static __host__ __device__ constexpr int y_elem(int row_in_group, int field) { return (field * 3 + row_in_group) * SW; }
     // RK4 parks two 3-row rings in shared memory (k2 and k3; classical opt-in: k1, k1+2k2, k1+2k2+2k3)
     static __host__ __device__ constexpr int k_rows(bool classical) { return NST == 4 ? (classical ? 9 : 6) : 0; }
-    static __host__ __device__ constexpr int smem_bytes(bool classical) { return (kRing + k_rows(classical)) * ROW_BYTES + kGroups * 8; }
+    // rings + one mbarrier per group + the three peer-push offsets (PeerExchange)
+    static __host__ __device__ constexpr int smem_bytes(bool classical) { return (kRing + k_rows(classical)) * ROW_BYTES + kGroups * 8 + 3 * 8; }
 };
 
 // One lane of the (converged) warp. With elect.sync the compiler knows exactly one lane runs the producer code, so
@@ -180,6 +187,8 @@ struct SweepT {
     static constexpr bool classical = NST == 4 && CL;  // textbook RK4 opt-in: its own kernel instantiation
     uint32_t ring_u32, bar_u32;
     bool st_vec, st_e[V], ragged;
+    bool push;              // band CTA with a neighbour: every stored row also goes into the neighbour's ghost rows
+    const long long *pdel;  // shared memory: byte offsets from this rank's output addresses to the peer's (u, v, h)
 
     // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
     static constexpr bool kPacked = std::is_same<T, float>::value && V % 2 == 0 && RECIP;
@@ -318,7 +327,7 @@ struct SweepT {
     }
 
     // po: this lane's output addresses (u, v, h) of the row being stored, advanced one row per iteration by run()
-    __device__ __forceinline__ void store_out(const Row<T, V> &o, T *const (&po)[3]) const {
+    __device__ __forceinline__ void store_rows(const Row<T, V> &o, T *const (&po)[3]) const {
         if (!ragged) {  // block-uniform: every lane is entirely inside or entirely outside the output range
             if (st_vec) {
 #pragma unroll
@@ -331,6 +340,15 @@ struct SweepT {
 #pragma unroll
                     for (int f = 0; f < 3; ++f) po[f][e] = o.f[f][e];
                 }
+        }
+    }
+    __device__ __forceinline__ void store_out(const Row<T, V> &o, T *const (&po)[3]) const {
+        store_rows(o, po);
+        if (push) {  // block-uniform; the same row into the neighbour's ghost rows (peer mapping over NVLink)
+            T *pp[3];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) pp[f] = reinterpret_cast<T *>(reinterpret_cast<char *>(po[f]) + pdel[f]);
+            store_rows(o, pp);
         }
     }
 
@@ -579,13 +597,13 @@ struct SweepT {
 // the previous step this CTA reads (c-1, c, c+1) and overwrites (c). A dependency that has not arrived after ~4 s is
 // a protocol bug: the CTA gives up waiting and raises the error word (mapped host memory), which the host turns into
 // an error at the next synchronisation -- wrong numbers reported loudly instead of a hung device.
-__device__ __forceinline__ void overlap_enter(unsigned *done, unsigned steps_so_far, unsigned *err) {
+__device__ __forceinline__ void overlap_enter(unsigned *done, unsigned steps_so_far, unsigned *err, int li, int nli) {
     if (!done) return;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!steps_so_far) return;
-    const unsigned *slot = done + (size_t)blockIdx.z * gridDim.y + blockIdx.y;
+    const unsigned *slot = done + (size_t)blockIdx.z * nli + li;  // li: position of this chunk row in ROW order
     const unsigned target = steps_so_far * gridDim.x;  // every strip of a chunk row, every step so far
-    const unsigned *lo = blockIdx.y > 0 ? slot - 1 : slot, *hi = blockIdx.y + 1 < gridDim.y ? slot + 1 : slot;
+    const unsigned *lo = li > 0 ? slot - 1 : slot, *hi = li + 1 < nli ? slot + 1 : slot;
     unsigned tries = 0;
     while (!__all_sync(kFull, (int)(ld_relaxed_gpu(lo) - target) >= 0 && (int)(ld_relaxed_gpu(slot) - target) >= 0 &&
                                   (int)(ld_relaxed_gpu(hi) - target) >= 0)) {
@@ -599,11 +617,31 @@ __device__ __forceinline__ void overlap_enter(unsigned *done, unsigned steps_so_
     fence_proxy_async_global();  // ... are read by the TMA engine (async proxy)
 }
 // leave: this CTA's rows are stored
-__device__ __forceinline__ void overlap_leave(unsigned *done) {
+__device__ __forceinline__ void overlap_leave(unsigned *done, int li, int nli) {
     if (!done) return;
     __syncwarp();
     fence_acq_rel_gpu();  // release
-    if (threadIdx.x == 0) atomicAdd(done + (size_t)blockIdx.z * gridDim.y + blockIdx.y, 1u);
+    if (threadIdx.x == 0) atomicAdd(done + (size_t)blockIdx.z * nli + li, 1u);
+}
+// Fused ghost exchange (PeerExchange): a band CTA waits until the neighbour's band of the previous step has landed in
+// this rank's ghost rows (flag in local memory, bumped over NVLink; same convergent polling as above) ...
+__device__ __forceinline__ void peer_wait(const unsigned *flag, unsigned target, unsigned *err) {
+    unsigned tries = 0;
+    while (!__all_sync(kFull, (int)(ld_relaxed_sys(flag) - target) >= 0)) {
+        __nanosleep(200);
+        if (++tries > 20000000u) {
+            if (err) *(volatile unsigned *)err = 2u;
+            break;
+        }
+    }
+    fence_acq_rel_sys();
+    fence_proxy_async_global();
+}
+// ... and tells the neighbour when its own rows have been stored over there
+__device__ __forceinline__ void peer_signal(unsigned *flag) {
+    __syncwarp();
+    fence_acq_rel_sys();  // release at system scope: the peer stores of every lane (ordered by the warp barrier)
+    if (threadIdx.x == 0) atomicAdd_system(flag, 1u);
 }
 
 template <typename T, int NST, int V, bool RECIP, int MINB, bool CL, bool FOLD>
@@ -615,14 +653,26 @@ __global__ void __launch_bounds__(32, MINB)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int strip = blockIdx.x;
-    // blockIdx.y enumerates the chunks of the first row range, then those of the optional second one
-    const int nchunks1 = (a.y_end - a.y_begin + rows_per_chunk - 1) / rows_per_chunk;
-    const bool second = (int)blockIdx.y >= nchunks1;
-    const int cy = second ? (int)blockIdx.y - nchunks1 : (int)blockIdx.y;
-    const int y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
-    const int y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
+    int y0, y1, li = (int)blockIdx.y, role = 0;  // role: 0 interior, 1 top band, 2 bottom band (PeerExchange)
+    const int nli = (int)gridDim.y;
+    if (a.px.band > 0) {
+        // fused ghost exchange: chunk rows are [top band | bottom band | interior chunks]; li = position in row order
+        if (blockIdx.y == 0) { y0 = 0; y1 = a.px.band; role = 1; li = 0; }
+        else if (blockIdx.y == 1) { y0 = g.H - a.px.band; y1 = g.H; role = 2; li = nli - 1; }
+        else { y0 = a.px.band + ((int)blockIdx.y - 2) * rows_per_chunk; y1 = min(y0 + rows_per_chunk, g.H - a.px.band); li = (int)blockIdx.y - 1; }
+    } else {
+        // blockIdx.y enumerates the chunks of the first row range, then those of the optional second one
+        const int nchunks1 = (a.y_end - a.y_begin + rows_per_chunk - 1) / rows_per_chunk;
+        const bool second = (int)blockIdx.y >= nchunks1;
+        const int cy = second ? (int)blockIdx.y - nchunks1 : (int)blockIdx.y;
+        y0 = (second ? a.y_begin2 : a.y_begin) + cy * rows_per_chunk;
+        y1 = min(y0 + rows_per_chunk, second ? a.y_end2 : a.y_end);
+    }
     if (strip * L::OUTW >= g.W || y0 >= y1) return;  // block-uniform (never taken when a.ovl_done is set: exact grid)
-    overlap_enter(a.ovl_done, a.ovl_target, a.ovl_err);
+    overlap_enter(a.ovl_done, a.ovl_target, a.ovl_err, li, nli);
+    const bool peer_up = role == 1 && a.px.up.u != nullptr, peer_dn = role == 2 && a.px.dn.u != nullptr;
+    if ((peer_up || peer_dn) && a.px.target)
+        peer_wait(a.px.wait + (peer_dn ? 1 : 0), a.px.target * gridDim.x * gridDim.z, a.ovl_err);
 
     SweepT<T, NST, V, RECIP, CL, FOLD> sw(g, ph, a);
     if constexpr (std::is_same<T, float>::value) {
@@ -660,6 +710,22 @@ __global__ void __launch_bounds__(32, MINB)
     }
     sw.st_vec = all_in;
     sw.ragged = V > 1 && ((sw.out_hi - sw.out_lo) % V != 0);
+    // peer push: byte offsets from this rank's output addresses to the same cell of the neighbour's ghost rows
+    // (rows [0, band) -> its rows [H_up, H_up + band); rows [H - band, H) -> its rows [-band, 0)), parked in shared memory
+    sw.push = peer_up || peer_dn;
+    long long *pdel = reinterpret_cast<long long *>(smem_raw + (kRing + L::k_rows(NST == 4 && CL)) * L::ROW_BYTES + kGroups * 8);
+    sw.pdel = pdel;
+    if (sw.push && lane < 3) {
+        const Planes3<T> &P = peer_up ? a.px.up : a.px.dn;
+        const int Hp = peer_up ? a.px.up_H : a.px.dn_H;
+        const T *mine = lane == 0 ? a.O.u : lane == 1 ? a.O.v : a.O.h;
+        const T *theirs = lane == 0 ? P.u : lane == 1 ? P.v : P.h;
+        const long long lstride_p = (long long)(Hp + 2 * kLeadRows) * g.pitch;
+        const long long shift = (long long)blockIdx.z * (lstride_p - g.level_stride) +
+                                (long long)(peer_up ? Hp : -g.H) * g.pitch;
+        pdel[lane] = (reinterpret_cast<const char *>(theirs) - reinterpret_cast<const char *>(mine)) +
+                     shift * (long long)sizeof(T);
+    }
 
     if (lane == 0) {
 #pragma unroll
@@ -671,18 +737,17 @@ __global__ void __launch_bounds__(32, MINB)
     __syncwarp();
     // RK4: CTAs away from every domain edge (the vast majority) run a loop body without any boundary handling
     // (0.578 -> 0.564 ms/step at 8192^2; no gain for the 1- and 2-stage kernels, which keep the single body)
-    // RK4: CTAs away from every domain edge (the vast majority) run a loop body without any boundary handling
-    // (0.578 -> 0.564 ms/step at 8192^2; no gain for the 1- and 2-stage kernels, which keep the single body)
     if constexpr (NST == 4) {
-        const bool pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax;
+        const bool pure = !sw.edge_strip && y0 - NST >= sw.gmin && y1 + NST <= sw.gmax && !sw.push;
         if (pure) {
             sw.template run<true>();
-            overlap_leave(a.ovl_done);  // this CTA's rows are stored: publish them to the next step's CTAs
+            overlap_leave(a.ovl_done, li, nli);  // this CTA's rows are stored: publish them to the next step's CTAs
             return;
         }
     }
     sw.template run<false>();
-    overlap_leave(a.ovl_done);
+    if (sw.push) peer_signal(peer_up ? a.px.sig_up : a.px.sig_dn);
+    overlap_leave(a.ovl_done, li, nli);
 }
 
 int env_int(const char *name, int dflt) {
@@ -695,10 +760,11 @@ int env_int(const char *name, int dflt) {
 // 0.456 at 160-192, 0.453 at 256; fp64 RK2 (16384^2) 2.23 / 2.09 / 2.11 ms at 64 / 128 / 192. The HBM-bound fp32
 // Euler kernel wants short chunks (0.257 / 0.260 / 0.282 / 0.313 ms at 64 / 88 / 128 / 192). Small grids get
 // shorter chunks so that there are at least about two CTAs per warp slot of the GPU.
-int rows_per_chunk_for(int nstages, bool f32, int W, int H, int L) {
+int rows_per_chunk_for(int nstages, bool f32, int W, int H, int L, bool overlapped) {
     static const int forced = env_int("WSB_FUSED_ROWS_PER_CHUNK", 0);
     if (forced > 0) return forced;
-    const int cap = f32 ? (nstages == 4 ? 256 : 64) : (nstages == 2 ? 128 : 64);
+    // without the step overlap the drain of tall chunks is exposed at every step (0.60 vs 0.51 ms at 256 vs 64 rows)
+    const int cap = !overlapped ? 64 : f32 ? (nstages == 4 ? 256 : 64) : (nstages == 2 ? 128 : 64);
     const int cols = f32 ? (nstages == 2 ? 120 : 56) : (nstages == 4 ? 24 : 60);  // output columns per strip
     const long long strips = (W + cols - 1) / cols;
     long long rpc = strips * (long long)H * L / (2 * 148 * 16);
@@ -745,8 +811,10 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     if (rows <= 0) return cudaSuccess;
     const int strips = (g.W + L::OUTW - 1) / L::OUTW;
     const int rpc = a.rows_per_chunk > 0 ? a.rows_per_chunk
-                                         : rows_per_chunk_for(NST, std::is_same<T, float>::value, g.W, g.H, g.L);
-    const int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
+                                         : rows_per_chunk_for(NST, std::is_same<T, float>::value, g.W, g.H, g.L, false);
+    int chunks = (rows + rpc - 1) / rpc + (rows2 > 0 ? (rows2 + rpc - 1) / rpc : 0);
+    if (a.px.band > 0)  // fused ghost exchange: [top band | bottom band | interior chunks] over the whole slab
+        chunks = 2 + (g.H - 2 * a.px.band + rpc - 1) / rpc;
     const dim3 grid(strips, chunks, g.L);
     CUtensorMap tu, tv, th;
     if (cudaError_t e = make_plane_map<T>(&tu, g, a.Y.u, L::SW)) return e;
@@ -785,9 +853,22 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
 
 }  // namespace
 
+// strips (CTAs per chunk row and level) of a launch: what one fused step adds to a neighbour's flag per level
+int step_tma_strips(int nstages, int dtype, int W) {
+    const bool f32 = dtype == WSB_F32;
+    int cols;
+    if (f32) cols = nstages == 1 ? (env_int("WSB_CELLS_PER_LANE", 2) == 4 ? Layout<float, 1, 4>::OUTW : Layout<float, 1, 2>::OUTW)
+                  : nstages == 2 ? (env_int("WSB_CELLS_PER_LANE", 4) == 2 ? Layout<float, 2, 2>::OUTW : Layout<float, 2, 4>::OUTW)
+                                 : Layout<float, 4, 2>::OUTW;
+    else cols = nstages == 1 ? (env_int("WSB_CELLS_PER_LANE", 2) == 1 ? Layout<double, 1, 1>::OUTW : Layout<double, 1, 2>::OUTW)
+                : nstages == 2 ? (env_int("WSB_CELLS_PER_LANE", 2) == 1 ? Layout<double, 2, 1>::OUTW : Layout<double, 2, 2>::OUTW)
+                               : Layout<double, 4, 1>::OUTW;
+    return (W + cols - 1) / cols;
+}
+
 // rows per chunk of a full-height launch: the host sizes the step-overlap counters with it (one per chunk row)
-int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L) {
-    return rows_per_chunk_for(nstages, dtype == WSB_F32, W, H, L);
+int step_tma_rows_per_chunk(int nstages, int dtype, int W, int H, int L, bool overlapped) {
+    return rows_per_chunk_for(nstages, dtype == WSB_F32, W, H, L, overlapped);
 }
 
 namespace {
