@@ -213,20 +213,32 @@ const Profile kPolar = {{1020.0f, 1018.0f, 1016.0f, 1014.0f, 1012.0f, 1010.0f, 1
                         {10.0f, 12.0f, 14.0f, 16.0f, 18.0f, 20.0f, 18.0f, 16.0f, 14.0f, 12.0f},
                         {0.0f, -1.0f, -2.0f, -3.0f, -4.0f, -3.0f, -2.0f, -1.0f, 0.0f, 1.0f}};
 
-int ic_atmospheric_profile(const char *profile, const HostFields &g) {  // :474-537
+const Profile &profile_by_name(const char *profile) {
     const std::string name = profile ? profile : "standard";
-    const Profile &pr = name == "tropical" ? kTropical : name == "polar" ? kPolar : kStandard;
+    return name == "tropical" ? kTropical : name == "polar" ? kPolar : kStandard;
+}
+// the table row a grid row reads, and the three x-dependent perturbations (initial_conditions.cpp:499-528); shared by
+// the cell-by-cell host evaluation below and the separable device fill (apply_separable)
+size_t profile_index(int y, int H) {
     const size_t n = 10;
+    const float y_norm = static_cast<float>(y) / (H - 1);
+    return std::min(static_cast<size_t>(y_norm * (n - 1)), n - 1);
+}
+void profile_column(int x, int W, float &t_var, float &p_var, float &q_var) {
+    const float x_norm = static_cast<float>(x) / (W - 1);
+    t_var = 2.0f * std::sin(2.0f * M_PI * x_norm);  // double product, rounded once on assignment
+    p_var = 2.0f * std::cos(2.0f * M_PI * x_norm);
+    q_var = 0.02f * std::sin(4.0f * M_PI * x_norm);
+}
+
+int ic_atmospheric_profile(const char *profile, const HostFields &g) {  // :474-537
+    const Profile &pr = profile_by_name(profile);
     for (int y = g.ys; y < g.ye; ++y) {
-        const float y_norm = static_cast<float>(y) / (g.H - 1);
-        size_t idx = static_cast<size_t>(y_norm * (n - 1));
-        idx = std::min(idx, n - 1);
+        const size_t idx = profile_index(y, g.H);
         const float t_base = pr.t[idx], p_base = pr.p[idx], q_base = pr.q[idx], u_base = pr.u[idx], v_base = pr.v[idx];
         for (int x = 0; x < g.W; ++x) {
-            const float x_norm = static_cast<float>(x) / (g.W - 1);
-            const float t_var = 2.0f * std::sin(2.0f * M_PI * x_norm);
-            const float p_var = 2.0f * std::cos(2.0f * M_PI * x_norm);
-            const float q_var = 0.02f * std::sin(4.0f * M_PI * x_norm);
+            float t_var, p_var, q_var;
+            profile_column(x, g.W, t_var, p_var, q_var);
             g.set(g.t, x, y, t_base + t_var);
             g.set(g.p, x, y, p_base + p_var);
             g.set(g.q, x, y, q_base + q_var);
@@ -289,6 +301,60 @@ int ic_dispatch_parallel(const char *name, const Params &a, std::mt19937 &rng, c
     return mask;
 }
 
+// ---- device-side path ------------------------------------------------------------------
+// Six of the nine initial conditions are separable: a constant (uniform), a function of the row alone (zonal_flow,
+// jet_stream, front -- their one libm call sits outside the x loop of the reference too), or table(y) + f(x) with one
+// fp32 addition per cell (the three atmospheric profiles). For those the host evaluates O(W + H) values with the
+// reference's own expressions (libm is part of the reference's results) and a kernel expands them in HBM: a 32768^2
+// grid never exists on the host and costs one sweep per written field at memory bandwidth. Returns 1 if handled.
+int apply_separable(wsb_grid *grid, const std::string &n, const Params &a, const char *profile, int W, int H, int row0,
+                    int Hglobal) {
+    const int fields[6] = {WSB_FIELD_U, WSB_FIELD_V, WSB_FIELD_HEIGHT, WSB_FIELD_PRESSURE, WSB_FIELD_TEMPERATURE,
+                           WSB_FIELD_HUMIDITY};
+    if (n == "uniform") {
+        const float val[6] = {a.get(0, 0.0f), a.get(1, 0.0f), a.get(2, 10.0f), a.get(3, 1000.0f), a.get(4, 300.0f),
+                              a.get(5, 0.0f)};
+        for (int k = 0; k < 6; ++k)
+            if (wsb::grid_fill_uniform(grid, fields[k], val[k]) != WSB_OK) return -1;
+        return 1;
+    }
+    const bool rows_only = n == "zonal_flow" || n == "jet_stream" || n == "front";
+    const bool prof = n == "atmospheric_profile" || n == "standard_atmosphere" || n == "tropical_atmosphere" ||
+                      n == "polar_atmosphere";
+    if (!rows_only && !prof) return 0;
+    std::vector<float> row[6];
+    for (auto &r : row) r.resize((size_t)H);
+    if (rows_only) {
+        // the reference's own row loop on a one-column grid: none of the three reads the width
+        const HostFields g{1, Hglobal, row0, row0 + H, row[0].data(), row[1].data(), row[2].data(), row[3].data(),
+                           row[4].data(), row[5].data()};
+        std::mt19937 unused;
+        const int mask = ic_dispatch(n.c_str(), a, unused, profile, g);
+        if (mask < 0) return -1;
+        for (int k = 0; k < 6; ++k)
+            if ((mask & (1 << k)) && wsb::grid_fill_separable(grid, fields[k], row[k].data(), nullptr) != WSB_OK) return -1;
+        return 1;
+    }
+    const Profile &pr = profile_by_name(n == "atmospheric_profile" ? profile
+                                        : n == "tropical_atmosphere" ? "tropical"
+                                        : n == "polar_atmosphere"    ? "polar"
+                                                                     : "standard");
+    std::vector<float> col[3];
+    for (auto &c : col) c.resize((size_t)W);
+    for (int x = 0; x < W; ++x) profile_column(x, W, col[0][x], col[1][x], col[2][x]);  // t, p, q perturbations
+    for (int y = 0; y < H; ++y) {
+        const size_t idx = profile_index(row0 + y, Hglobal);
+        row[0][y] = pr.u[idx]; row[1][y] = pr.v[idx]; row[3][y] = pr.p[idx]; row[4][y] = pr.t[idx]; row[5][y] = pr.q[idx];
+    }
+    if (wsb::grid_fill_separable(grid, WSB_FIELD_U, row[0].data(), nullptr) != WSB_OK ||
+        wsb::grid_fill_separable(grid, WSB_FIELD_V, row[1].data(), nullptr) != WSB_OK ||
+        wsb::grid_fill_separable(grid, WSB_FIELD_TEMPERATURE, row[4].data(), col[0].data()) != WSB_OK ||
+        wsb::grid_fill_separable(grid, WSB_FIELD_PRESSURE, row[3].data(), col[1].data()) != WSB_OK ||
+        wsb::grid_fill_separable(grid, WSB_FIELD_HUMIDITY, row[5].data(), col[2].data()) != WSB_OK)
+        return -1;
+    return 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -320,24 +386,53 @@ int wsb_ic_apply(wsb_grid *grid, const char *name, const double *params, int32_t
     wsb::grid_slab_position(grid, &row0, &Hglobal);
     std::mt19937 rng(static_cast<int>(seed));
     rng.discard(3ULL * (unsigned long long)row0 * (unsigned long long)gi.width);  // "random": 3 draws per cell
-    // Evaluate and upload in row blocks: host memory stays bounded (a 32768^2 grid is 4 GiB per field) and
-    // fields an initial condition does not write are neither allocated nor touched on the device.
+    // separable initial conditions are expanded on the device from O(W + H) host values
+    if (!std::getenv("WSB_IC_HOST")) {
+        const int handled = apply_separable(grid, name ? name : "", a, profile, gi.width, gi.height, row0, Hglobal);
+        if (handled < 0) return WSB_ERR_CUDA;  // the message is the failing call's
+        if (handled > 0) return wsb_grid_calculate_diagnostics(grid);
+    }
+    // The others (vortex, mountain, breaking_wave: libm per cell; random: the mt19937 stream) are evaluated by host
+    // threads in row blocks -- host memory stays bounded (a 32768^2 grid is 4 GiB per field) and fields an initial
+    // condition does not write are neither allocated nor touched on the device -- through two page-locked buffer sets:
+    // block k uploads while block k+1 is evaluated.
     const int block = std::max(1, std::min(gi.height, (int)(((size_t)32 << 20) / sizeof(float) / (size_t)gi.width)));
     const int fields[6] = {WSB_FIELD_U, WSB_FIELD_V, WSB_FIELD_HEIGHT, WSB_FIELD_PRESSURE, WSB_FIELD_TEMPERATURE,
                            WSB_FIELD_HUMIDITY};
-    std::vector<float> buf[6];
-    for (auto &b : buf) b.resize((size_t)block * gi.width);
-    for (int ys = 0; ys < gi.height; ys += block) {
-        const int ye = std::min(gi.height, ys + block);
-        const HostFields g{gi.width, Hglobal, row0 + ys, row0 + ye, buf[0].data(), buf[1].data(), buf[2].data(),
-                           buf[3].data(), buf[4].data(), buf[5].data()};
-        const int mask = ic_dispatch_parallel(name, a, rng, profile, g);
-        if (mask < 0)
-            return wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
-        for (int k = 0; k < 6; ++k)
-            if (mask & (1 << k))  // every level receives the same 2-D initial condition (the reference has one level)
-                WSB_TRY(wsb::grid_upload_rows(grid, fields[k], buf[k].data(), ys, ye - ys));
+    const size_t block_floats = (size_t)block * gi.width;
+    const int nsets = gi.height > block ? 2 : 1;
+    float *pin = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    if (cudaMallocHost((void **)&pin, sizeof(float) * block_floats * 6 * nsets) != cudaSuccess) {
+        cudaGetLastError();
+        return wsb::fail(WSB_ERR_OUT_OF_MEMORY, "initial condition: cannot allocate the page-locked staging buffers");
     }
+    for (int k = 0; k < nsets; ++k) cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+    int status = WSB_OK, nblk = 0;
+    for (int ys = 0; ys < gi.height && status == WSB_OK; ys += block, ++nblk) {
+        const int ye = std::min(gi.height, ys + block), set = nblk % nsets;
+        float *b = pin + (size_t)set * 6 * block_floats;
+        if (nblk >= nsets) cudaEventSynchronize(done[set]);  // the upload that last read this buffer set
+        const HostFields g{gi.width, Hglobal, row0 + ys, row0 + ye, b, b + block_floats, b + 2 * block_floats,
+                           b + 3 * block_floats, b + 4 * block_floats, b + 5 * block_floats};
+        const int mask = ic_dispatch_parallel(name, a, rng, profile, g);
+        if (mask < 0) {
+            status = wsb::fail(WSB_ERR_INVALID_ARGUMENT, std::string("unknown initial condition '") + (name ? name : "") + "'");
+            break;
+        }
+        for (int k = 0; k < 6 && status == WSB_OK; ++k)
+            if (mask & (1 << k))  // every level receives the same 2-D initial condition (the reference has one level)
+                status = wsb::grid_upload_rows_async(grid, fields[k], b + (size_t)k * block_floats, ys, ye - ys);
+        if (status == WSB_OK) status = wsb::grid_record_event(grid, done[set]);
+    }
+    for (int k = 0; k < nsets; ++k) {
+        if (done[k]) {
+            cudaEventSynchronize(done[k]);
+            cudaEventDestroy(done[k]);
+        }
+    }
+    cudaFreeHost(pin);
+    if (status != WSB_OK) return status;
     // every reference initial condition ends with grid.calculateDiagnostics()
     return wsb_grid_calculate_diagnostics(grid);
 }

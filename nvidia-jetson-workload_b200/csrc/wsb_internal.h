@@ -147,6 +147,10 @@ cudaError_t launch_axpy_const2(const Geometry<T> &g, const T *ta, T *to, const T
 template <typename T>
 cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st);
 
+// field(x, y) = rowv[y] (+ colv[x], one fp32 addition) on every level: separable initial conditions (wsb_ic.cpp)
+template <typename T>
+cudaError_t launch_expand_separable(const Geometry<T> &g, T *p, const float *rowv, const float *colv, cudaStream_t st);
+
 // per-block partial sums of mass and energy in double; partial[2*b], partial[2*b+1]
 template <typename T>
 cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, const T *h, double gravity,
@@ -169,6 +173,15 @@ int step_tma_strips(int nstages, int dtype, int W);
 // rows [y0, y0+nrows) of a field from a dense float host block (nrows x W), replicated to every level and
 // converted to the grid's dtype (wsb_sim.cu; used by the blockwise initial conditions)
 int grid_upload_rows(wsb_grid *grid, int field, const float *host_rows, int y0, int nrows);
+// same, asynchronous: host_rows must be page-locked and stay untouched until *done_event (recorded on the grid's
+// stream behind the copies) has completed
+int grid_upload_rows_async(wsb_grid *grid, int field, const float *host_rows, int y0, int nrows);
+int grid_record_event(wsb_grid *grid, cudaEvent_t ev);
+// a whole field from host vectors of the reference's float values: field(x, y) = rowv[y] (+ colv[x]); rowv covers this
+// grid's rows, colv (may be null) its columns
+int grid_fill_separable(wsb_grid *grid, int field, const float *rowv, const float *colv);
+// a whole field set to one value (all levels)
+int grid_fill_uniform(wsb_grid *grid, int field, float value);
 // where this grid sits in the global domain (row slab of a decomposed simulation; else 0 and its own height)
 void grid_slab_position(const wsb_grid *grid, int *row0, int *global_height);
 

@@ -269,6 +269,26 @@ cudaError_t launch_axpy_const2(const Geometry<T> &g, const T *ta, T *to, const T
     return cudaGetLastError();
 }
 
+// Separable initial conditions (wsb_ic.cpp): field(x, y) = rowv[y] (+ colv[x]). The vectors hold the reference's own
+// float values (evaluated on the host with libm, O(W + H) work); the sum is ONE fp32 addition per cell, exactly the
+// reference's `base + var` (initial_conditions.cpp:520-528), then widened for fp64 grids. Every level gets the field.
+template <typename T>
+__global__ void __launch_bounds__(kBX *kBY)
+    expand_separable_kernel(const Geometry<T> g, T *__restrict__ p, const float *__restrict__ rowv,
+                            const float *__restrict__ colv) {
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const float v = colv ? __fadd_rn(rowv[y], colv[x]) : rowv[y];
+    p[(long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x] = (T)v;
+}
+
+template <typename T>
+cudaError_t launch_expand_separable(const Geometry<T> &g, T *p, const float *rowv, const float *colv, cudaStream_t st) {
+    expand_separable_kernel<T><<<grid_for(g, g.H, g.W), dim3(kBX, kBY), 0, st>>>(g, p, rowv, colv);
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_fill(const Geometry<T> &g, T *p, T value, bool with_halo, cudaStream_t st) {
     const int halo = with_halo ? kHaloRows : 0;
@@ -292,6 +312,8 @@ cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, con
     template cudaError_t launch_axpy_const2<T>(const Geometry<T> &, const T *, T *, const T *, T *, T, T, T,         \
                                                cudaStream_t);                                                       \
     template cudaError_t launch_fill<T>(const Geometry<T> &, T *, T, bool, cudaStream_t);                            \
+    template cudaError_t launch_expand_separable<T>(const Geometry<T> &, T *, const float *, const float *,          \
+                                                    cudaStream_t);                                                   \
     template cudaError_t launch_mass_energy<T>(const Geometry<T> &, const T *, const T *, const T *, double,         \
                                                double *, int, cudaStream_t);
 WSB_INSTANTIATE(float)

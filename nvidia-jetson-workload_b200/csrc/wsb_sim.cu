@@ -710,6 +710,66 @@ int grid_upload_rows(wsb_grid *g, int field, const float *host_rows, int y0, int
     return WSB_OK;
 }
 
+// the bookkeeping every write into a field of the grid shares
+static int grid_prepare_write(wsb_grid *g, int field) {
+    WSB_CUDA(cudaSetDevice(g->device));
+    if (g->owner && field <= WSB_FIELD_V) WSB_TRY(sim_materialize_diagnostics(g->owner));
+    if (!g->f[field].base) WSB_TRY(grid_alloc_plane(g, &g->f[field].base));
+    if (g->owner && field <= WSB_FIELD_HEIGHT) {
+        g->owner->halo_valid = false;
+        g->owner->ghosts_in_flight = false;
+    }
+    return WSB_OK;
+}
+
+int grid_record_event(wsb_grid *g, cudaEvent_t ev) {
+    WSB_CUDA(cudaEventRecord(ev, g->stream));
+    return WSB_OK;
+}
+
+int grid_upload_rows_async(wsb_grid *g, int field, const float *host_rows, int y0, int nrows) {
+    if (!g || !host_rows || field < 0 || field > WSB_FIELD_HUMIDITY || y0 < 0 || nrows <= 0 || y0 + nrows > g->H)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "bad row block");
+    if (g->dtype != WSB_F32) return grid_upload_rows(g, field, host_rows, y0, nrows);  // widened through a host copy
+    WSB_TRY(grid_materialize(g, field));
+    WSB_TRY(grid_prepare_write(g, field));
+    const size_t es = sizeof(float);
+    for (int l = 0; l < g->L; ++l) {
+        char *dst = (char *)g->origin(field) + ((size_t)l * g->level_stride + (size_t)y0 * g->pitch) * es;
+        WSB_CUDA(copy_rows(dst, (size_t)g->pitch * es, host_rows, (size_t)g->W * es, (size_t)g->W * es, (size_t)nrows,
+                           cudaMemcpyHostToDevice, g->stream));
+    }
+    return WSB_OK;
+}
+
+int grid_fill_uniform(wsb_grid *g, int field, float value) {
+    if (!g || field < 0 || field > WSB_FIELD_HUMIDITY) return fail(WSB_ERR_INVALID_ARGUMENT, "bad field");
+    WSB_TRY(grid_prepare_write(g, field));
+    if (g->dtype == WSB_F64) WSB_CUDA(launch_fill<double>(g->geom<double>(), (double *)g->origin(field), (double)value, false, g->stream));
+    else WSB_CUDA(launch_fill<float>(g->geom<float>(), (float *)g->origin(field), value, false, g->stream));
+    return WSB_OK;
+}
+
+int grid_fill_separable(wsb_grid *g, int field, const float *rowv, const float *colv) {
+    if (!g || !rowv || field < 0 || field > WSB_FIELD_HUMIDITY) return fail(WSB_ERR_INVALID_ARGUMENT, "bad field");
+    WSB_TRY(grid_prepare_write(g, field));
+    float *dev = nullptr;
+    WSB_CUDA(cudaMalloc(&dev, sizeof(float) * ((size_t)g->H + (colv ? g->W : 0))));
+    cudaError_t e = cudaMemcpyAsync(dev, rowv, sizeof(float) * g->H, cudaMemcpyHostToDevice, g->stream);
+    if (e == cudaSuccess && colv)
+        e = cudaMemcpyAsync(dev + g->H, colv, sizeof(float) * g->W, cudaMemcpyHostToDevice, g->stream);
+    if (e == cudaSuccess) {
+        if (g->dtype == WSB_F64)
+            e = launch_expand_separable<double>(g->geom<double>(), (double *)g->origin(field), dev, colv ? dev + g->H : nullptr, g->stream);
+        else
+            e = launch_expand_separable<float>(g->geom<float>(), (float *)g->origin(field), dev, colv ? dev + g->H : nullptr, g->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);  // the vectors are the caller's, the scratch is freed here
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "separable initial condition", __FILE__, __LINE__);
+    return WSB_OK;
+}
+
 }  // namespace wsb
 
 // ------------------------------------------------------------------------------ C-ABI: misc --
