@@ -58,6 +58,12 @@ WORKLOADS = {
                             scaling="weak", metric="grid cell-updates/sec (RK4 SWE step)", dx=0.8, dy=1.7,
                             desc="SWE {W}x{H} fp32 RK4, dx=0.8 dy=1.7 (true-division kernels)", bpc_stage=168,
                             bpc_step=24),
+    # NOT a reference configuration: the extended physics opt-in (beta plane + viscosity + diffusivity), textbook RK4
+    "swe8192_rk4_ext": dict(W=8192, rows=8192, model="shallow_water", integ="rk4", dtype="f32", levels=1,
+                            scaling="weak", metric="grid cell-updates/sec (RK4 step, extended physics)",
+                            extended=(1.0e-5, 0.05, 0.02), classical=True,
+                            desc="beta-plane shallow water with viscosity/diffusivity {W}x{H} fp32, textbook RK4 "
+                                 "(WSB_PHYSICS_EXTENDED: not in the reference)", bpc_stage=192, bpc_step=24),
     "swe32768_rk4": dict(W=32768, rows=32768, model="shallow_water", integ="rk4", dtype="f32", levels=1,
                          scaling="strong", metric="grid cell-updates/sec (RK4 SWE step)",
                          desc="SWE {W}x{H} fp32 RK4 (reference-parity combine), strong scaling",
@@ -308,7 +314,8 @@ def run_b200_arm(args, wl, rank, world, local_rank):
         sim = _capi.Simulation(w["W"], H_global, model=w["model"], integrator=w["integ"], coriolis_f=0.1, max_time=1e30,
                                dtype=np_dtype, num_levels=w["levels"], kernel=kernel or args.kernel,
                                device_id=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, arith=arith,
-                               dx=w.get("dx", 1.0), dy=w.get("dy", 1.0))
+                               dx=w.get("dx", 1.0), dy=w.get("dy", 1.0), extended=w.get("extended"),
+                               rk4_classical=w.get("classical", False))
         return sim, H_global, np_dtype
 
     def time_device(sim, steps, warmup):
@@ -471,7 +478,7 @@ def run_b200_arm(args, wl, rank, world, local_rank):
     if not args.no_other_configs and args.workload == "swe8192_rk4":
         if world == 1:
             for name, arith in (("swe8192_euler", "strict"), ("baro16384_f64", "strict"), ("prim2048x64", "strict"),
-                                ("swe8192_rk4_div", "strict"), ("swe8192_rk4", "folded")):
+                                ("swe8192_rk4_div", "strict"), ("swe8192_rk4", "folded"), ("swe8192_rk4_ext", "strict")):
                 others.append(sub_line(name, arith))
         strong = sub_line("swe32768_rk4", "strict", steps=max(5, min(args.steps, 10)))
 

@@ -89,6 +89,18 @@ typedef enum wsb_arith_mode {
                              overflow; the sign of a zero tendency may differ. Ignored where it does not apply. */
 } wsb_arith_mode;
 
+/* Which tendencies the models evaluate. */
+typedef enum wsb_physics_mode {
+    WSB_PHYSICS_REFERENCE = 0, /* the reference's: every model is the shallow-water stencil (ws.cpp:473-560) */
+    WSB_PHYSICS_EXTENDED = 1   /* NOT in the reference's compute code (non-parity opt-in; the oracle's own
+                                  restatement is the specification, oracle/ws_oracle_body.inc): the barotropic model
+                                  the reference advertises and stubs (README.md:7-13, ws.cpp:542-550), in
+                                  primitive-variable form -- shallow-water tendencies on a beta plane
+                                  f(y) = coriolis_f + beta*dy*(y - (H-1)/2), eddy viscosity on u, v and
+                                  diffusivity on h (5-point Laplacian, same clamped neighbours). Applies to
+                                  every model and integrator; power-of-two spacing on the whole-step kernels. */
+} wsb_physics_mode;
+
 /* Which hand-written sm_100a path advances the state. All variants produce bit-identical results. */
 typedef enum wsb_kernel_variant {
     WSB_KERNEL_AUTO = 0,           /* best available for the configuration */
@@ -124,7 +136,11 @@ typedef struct wsb_config {
     int32_t nranks;
     const void *nccl_unique_id; /* WSB_NCCL_UNIQUE_ID_BYTES bytes from wsb_nccl_get_unique_id on rank 0 */
     int32_t arith_mode;         /* wsb_arith_mode (0 = strict, the default) */
-    int32_t reserved[7];
+    int32_t physics_mode;       /* wsb_physics_mode (0 = the reference's tendencies, the default) */
+    int32_t reserved[6];
+    /* SimulationConfig.beta / viscosity / diffusivity (ws.hpp:172-175): read by WSB_PHYSICS_EXTENDED only -- the
+     * reference never reads them, and neither does the default mode. */
+    double beta, viscosity, diffusivity;
 } wsb_config;
 
 #define WSB_NCCL_UNIQUE_ID_BYTES 128

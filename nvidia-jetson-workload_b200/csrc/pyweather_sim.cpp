@@ -85,6 +85,7 @@ struct SimulationConfig {  // weather_sim.hpp:155-191, same defaults
     bool rk4_classical = false;
     int kernel_variant = WSB_KERNEL_AUTO;
     bool folded_arithmetic = false;  // wsb_arith_mode: WSB_ARITH_FOLDED (opt-in, see include/weather_b200.h)
+    bool extended_physics = false;   // wsb_physics_mode: WSB_PHYSICS_EXTENDED -- beta, viscosity, diffusivity are READ
     // row-slab decomposition over the GPUs of one box (one process per GPU): this process is `rank` of `nranks`,
     // grid_height is the GLOBAL height, nccl_unique_id the 128 bytes of pyweather_sim.nccl_unique_id() made on rank 0
     // and handed to every rank (e.g. torch.distributed.broadcast_object_list / mpi4py bcast)
@@ -394,6 +395,10 @@ public:
         c.rk4_mode = config.rk4_classical ? WSB_RK4_CLASSICAL : WSB_RK4_REFERENCE;
         c.kernel_variant = config.kernel_variant;
         c.arith_mode = config.folded_arithmetic ? WSB_ARITH_FOLDED : WSB_ARITH_STRICT;
+        c.physics_mode = config.extended_physics ? WSB_PHYSICS_EXTENDED : WSB_PHYSICS_REFERENCE;
+        c.beta = config.beta;
+        c.viscosity = config.viscosity;
+        c.diffusivity = config.diffusivity;
         c.rank = config.rank;
         c.nranks = config.nranks;
         if (config.nranks > 1) {
@@ -659,6 +664,7 @@ PYBIND11_MODULE(pyweather_sim, m) {
         .def_readwrite("rk4_classical", &SimulationConfig::rk4_classical)
         .def_readwrite("kernel_variant", &SimulationConfig::kernel_variant)
         .def_readwrite("folded_arithmetic", &SimulationConfig::folded_arithmetic)
+        .def_readwrite("extended_physics", &SimulationConfig::extended_physics)
         .def_readwrite("rank", &SimulationConfig::rank)
         .def_readwrite("nranks", &SimulationConfig::nranks)
         .def_property(

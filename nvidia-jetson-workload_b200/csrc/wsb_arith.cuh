@@ -92,6 +92,38 @@ __device__ __forceinline__ void tendency_cell(const Physics<T> &ph, T u, T v, T 
     dh = A::sub(A::sub(A::mul(-h, A::add(ux, vy)), A::mul(u, hx)), A::mul(v, hy));
 }
 
+// Extended physics for one cell: the tendencies above on a beta plane plus viscosity / diffusivity. fy is the row's
+// Coriolis parameter (ext_coriolis). Operation order: oracle/ws_oracle_body.inc (the specification of this mode).
+template <typename T>
+__device__ __forceinline__ T ext_coriolis(const Physics<T> &ph, int global_row) {
+    using A = Ar<T>;
+    return A::add(ph.f, A::mul(ph.bdy, A::sub((T)global_row, ph.yc)));
+}
+template <typename T>
+__device__ __forceinline__ T ext_laplacian(const Physics<T> &ph, T c, T l, T r, T u, T d) {
+    using A = Ar<T>;
+    const T two_c = A::mul(T(2), c);
+    const T tx = A::add(A::sub(r, two_c), l), ty = A::add(A::sub(d, two_c), u);
+    return A::add(A::mul(tx, ph.idx2), A::mul(ty, ph.idy2));
+}
+template <typename T, bool RECIP>
+__device__ __forceinline__ void tendency_cell_ext(const Physics<T> &ph, T fy, T u, T v, T h, T uL, T uR, T uU, T uD,
+                                                  T vL, T vR, T vU, T vD, T hL, T hR, T hU, T hD, T &du, T &dv, T &dh) {
+    using A = Ar<T>;
+    const T ux = cdiff<T, RECIP>(uR, uL, ph.ddx, ph.rdx);
+    const T uy = cdiff<T, RECIP>(uD, uU, ph.ddy, ph.rdy);
+    const T vx = cdiff<T, RECIP>(vR, vL, ph.ddx, ph.rdx);
+    const T vy = cdiff<T, RECIP>(vD, vU, ph.ddy, ph.rdy);
+    const T hx = cdiff<T, RECIP>(hR, hL, ph.ddx, ph.rdx);
+    const T hy = cdiff<T, RECIP>(hD, hU, ph.ddy, ph.rdy);
+    const T a = A::add(A::sub(A::sub(A::mul(-u, ux), A::mul(v, uy)), A::mul(ph.g, hx)), A::mul(fy, v));
+    const T b = A::sub(A::sub(A::sub(A::mul(-u, vx), A::mul(v, vy)), A::mul(ph.g, hy)), A::mul(fy, u));
+    const T c = A::sub(A::sub(A::mul(-h, A::add(ux, vy)), A::mul(u, hx)), A::mul(v, hy));
+    du = A::add(a, A::mul(ph.nu, ext_laplacian<T>(ph, u, uL, uR, uU, uD)));
+    dv = A::add(b, A::mul(ph.nu, ext_laplacian<T>(ph, v, vL, vR, vU, vD)));
+    dh = A::add(c, A::mul(ph.kappa, ext_laplacian<T>(ph, h, hL, hR, hU, hD)));
+}
+
 // y + c*k  (weather_simulation.cpp:187, 249, 381 ...: `0.5f * dt_ * k` is (0.5f*dt_)*k, c is pre-rounded)
 template <typename T>
 __device__ __forceinline__ T axpy(T y, T c, T k) {
@@ -205,6 +237,40 @@ __device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F
     // dh = (((-h)*(ux+vy)) - (u*hx)) - (v*hy);  ux + vy == vy - nux;  (-P) - Q == (-Q) - P
     const F2 s = f2_sub_prod(vy, nux);
     dh = f2_sub_prod(f2_sub_prod(f2_mul(u, nhx), f2_mul(h, s)), f2_mul(v, hy));
+}
+
+// Extended physics, packed (exact-reciprocal spacing): tendency_pair with the row's Coriolis parameter instead of the
+// constant f, plus nu*lap(u), nu*lap(v), kappa*lap(h). Same operations as tendency_cell_ext<float, true>, bit for bit:
+// (a - 2c) is c2 := (-2)*c subtracted as a product, p*idx2 + q*idy2 is p*idx2 - q*(-idy2), a + nu*L is a - (-nu)*L.
+struct PhysicsExtF2 {
+    F2 idx2, nidy2, nnu, nkappa;
+};
+__device__ __forceinline__ PhysicsExtF2 physics_ext_f2(const Physics<float> &ph) {
+    PhysicsExtF2 p;
+    p.idx2 = f2_splat(ph.idx2);
+    p.nidy2 = f2_splat(-ph.idy2);
+    p.nnu = f2_splat(-ph.nu);
+    p.nkappa = f2_splat(-ph.kappa);
+    return p;
+}
+__device__ __forceinline__ F2 ext_laplacian_pair(const PhysicsExtF2 &pe, F2 c, float lft, float rgt, F2 up, F2 dn) {
+    const F2 two_c = f2_mul(f2_splat(2.0f), c);
+    // horizontal: (R - 2c) + L per cell, scalar (the neighbours sit in different registers of the pair)
+    const F2 tx = F2{__fadd_rn(__fsub_rn(c.y, two_c.x), lft), __fadd_rn(__fsub_rn(rgt, two_c.y), c.x)};
+    const F2 ty = f2_add_packed(f2_sub_prod(dn, two_c), up);
+    return f2_sub_prod(f2_mul(tx, pe.idx2), f2_mul(ty, pe.nidy2));
+}
+__device__ __forceinline__ void tendency_pair_ext(const PhysicsF2 &ph, const PhysicsExtF2 &pe, float fy, F2 u, F2 v, F2 h,
+                                                  float uLft, float uRgt, F2 uU, F2 uD, float vLft, float vRgt, F2 vU,
+                                                  F2 vD, float hLft, float hRgt, F2 hU, F2 hD, F2 &du, F2 &dv, F2 &dh) {
+    PhysicsF2 row = ph;  // the row's Coriolis parameter replaces the constant one
+    row.f = f2_splat(fy);
+    row.nf = f2_splat(-fy);
+    F2 a, b, c;
+    tendency_pair(row, u, v, h, uLft, uRgt, uU, uD, vLft, vRgt, vU, vD, hLft, hRgt, hU, hD, a, b, c);
+    du = f2_sub_prod(a, f2_mul(pe.nnu, ext_laplacian_pair(pe, u, uLft, uRgt, uU, uD)));
+    dv = f2_sub_prod(b, f2_mul(pe.nnu, ext_laplacian_pair(pe, v, vLft, vRgt, vU, vD)));
+    dh = f2_sub_prod(c, f2_mul(pe.nkappa, ext_laplacian_pair(pe, h, hLft, hRgt, hU, hD)));
 }
 
 // ---- folded mode (opt-in, WSB_ARITH_FOLDED): dx == dy and 2dx a power of two, r = 1/(2dx) ---------------------

@@ -67,6 +67,11 @@ struct Physics {
                    // three-operation division, or 0 = plain IEEE division (wsb_arith.cuh)
     T g, f;
     int recip;     // 1: (a-b)*rdx is bit-identical to (a-b)/ddx for every input
+    // Extended physics (WSB_PHYSICS_EXTENDED; NOT in the reference's compute code, see include/weather_b200.h): beta
+    // plane f(y) = f + bdy*(y - yc), eddy viscosity nu on u, v, diffusivity kappa on h, 5-point Laplacian scaled by
+    // idx2 = 1/dx^2, idy2 = 1/dy^2. All constants are rounded once on the host, in T, as oracle/ws_oracle_body.inc does.
+    int ext;
+    T bdy, yc, nu, kappa, idx2, idy2;
 };
 
 // One fused RK stage: k = tend(S); then either

@@ -31,6 +31,11 @@ __global__ void __launch_bounds__(kBX *kBY)
 
     const T u = a.S.u[i], v = a.S.v[i], h = a.S.h[i];
     T du, dv, dh;
+    if (ph.ext)  // extended physics (uniform): beta plane + viscosity / diffusivity on the same clamped neighbours
+        tendency_cell_ext<T, RECIP>(ph, ext_coriolis<T>(ph, gy), u, v, h, a.S.u[iL], a.S.u[iR], a.S.u[iU], a.S.u[iD],
+                                    a.S.v[iL], a.S.v[iR], a.S.v[iU], a.S.v[iD], a.S.h[iL], a.S.h[iR], a.S.h[iU],
+                                    a.S.h[iD], du, dv, dh);
+    else
     tendency_cell<T, RECIP>(ph, u, v, h, a.S.u[iL], a.S.u[iR], a.S.u[iU], a.S.u[iD], a.S.v[iL], a.S.v[iR], a.S.v[iU],
                             a.S.v[iD], a.S.h[iL], a.S.h[iR], a.S.h[iU], a.S.h[iD], du, dv, dh);
     if (STORE_K) {

@@ -147,6 +147,8 @@ struct wsb_grid {
         p.rdy = (T)rdy;
         p.g = (T)gravity;
         p.f = (T)coriolis;
+        p.ext = 0;
+        p.bdy = p.yc = p.nu = p.kappa = p.idx2 = p.idy2 = T(0);
         return p;
     }
 };
@@ -340,6 +342,24 @@ static int effective_stages(const wsb_config &c) {
     }
 }
 
+// Physics of one tendency evaluation for this simulation: the grid's spacing + the configuration's constants
+// (+ the extended-physics constants, each rounded once in T exactly as oracle/ws_oracle_body.inc computes them)
+template <typename T>
+static Physics<T> sim_physics(const wsb_sim *s) {
+    Physics<T> p = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    p.ext = s->cfg.physics_mode == WSB_PHYSICS_EXTENDED;
+    if (p.ext) {
+        const T dx = (T)s->cur.dx, dy = (T)s->cur.dy;
+        p.idx2 = T(1.0f) / (dx * dx);
+        p.idy2 = T(1.0f) / (dy * dy);
+        p.bdy = (T)s->cfg.beta * dy;
+        p.yc = (T)(s->cfg.grid_height - 1) * T(0.5f);
+        p.nu = (T)s->cfg.viscosity;
+        p.kappa = (T)s->cfg.diffusivity;
+    }
+    return p;
+}
+
 // ghost-row exchange of 3 planes on the comm stream, ordered after `after` and signalling ev_halo
 static int sim_exchange(wsb_sim *s, void *const p[3], int nrows_halo, cudaEvent_t after) {
     if (!s->comm) return WSB_OK;
@@ -359,7 +379,7 @@ static int sim_exchange(wsb_sim *s, void *const p[3], int nrows_halo, cudaEvent_
 template <typename T>
 static int enqueue_stage(wsb_sim *s, StageArgs<T> a, void *const out_planes[3], bool exchange_output) {
     const Geometry<T> g = s->cur.geom<T>();
-    const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    const Physics<T> ph = sim_physics<T>(s);
     const int H = s->cur.H;
     if (!s->comm) {
         a.y_begin = 0;
@@ -461,7 +481,7 @@ static StepArgs<T> step_args(const wsb_sim *s) {
 template <typename T>
 static int enqueue_step_fused(wsb_sim *s, bool chain) {
     const Geometry<T> g = s->cur.geom<T>();
-    const Physics<T> ph = s->cur.physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    const Physics<T> ph = sim_physics<T>(s);
     StepArgs<T> a = step_args<T>(s);
     const int H = s->cur.H;
     const int halo = s->nstages;  // one ghost row per fused stage
@@ -1110,6 +1130,8 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
     if (c.model < 0 || c.model > WSB_MODEL_GENERAL) return fail(WSB_ERR_INVALID_ARGUMENT, "unknown model");
     if (c.integration_method < 0 || c.integration_method > WSB_INT_SEMI_IMPLICIT)
         return fail(WSB_ERR_INVALID_ARGUMENT, "unknown integration method");
+    if (c.physics_mode != WSB_PHYSICS_REFERENCE && c.physics_mode != WSB_PHYSICS_EXTENDED)
+        return fail(WSB_ERR_INVALID_ARGUMENT, "unknown physics_mode");
     if (c.arith_mode != WSB_ARITH_STRICT && c.arith_mode != WSB_ARITH_FOLDED)
         return fail(WSB_ERR_INVALID_ARGUMENT, "unknown arith_mode");
     if (const char *e = std::getenv("WSB_ARITH"))  // A/B runs: WSB_ARITH=folded|strict overrides the configuration
@@ -1126,6 +1148,8 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
     if (c.dtype == WSB_F32) {  // the reference's config fields are float (weather_sim.hpp:166-172)
         s->cfg.dt = (double)(float)c.dt; s->cfg.gravity = (double)(float)c.gravity;
         s->cfg.coriolis_f = (double)(float)c.coriolis_f; s->cfg.max_time = (double)(float)c.max_time;
+        s->cfg.beta = (double)(float)c.beta; s->cfg.viscosity = (double)(float)c.viscosity;
+        s->cfg.diffusivity = (double)(float)c.diffusivity;
     }
     s->dt = s->cfg.dt;
     s->nstages = effective_stages(c);
@@ -1163,8 +1187,11 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         // kernel path. The whole-step kernels implement the reference (aliased) RK4 combine only.
         int want = c.kernel_variant;
         const bool classical4 = s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL;
-        const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4;
-        const bool tma_ok = step_tma_supported(s->nstages, s->dtype);  // incl. the classical RK4 opt-in
+        // extended physics: whole-step TMA kernel on power-of-two spacing, else the per-stage kernel (any spacing)
+        const bool ext = c.physics_mode == WSB_PHYSICS_EXTENDED;
+        const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4 && !ext;
+        const bool tma_ok = step_tma_supported(s->nstages, s->dtype) &&  // incl. the classical RK4 opt-in
+                            (!ext || (is_pow2(2.0 * (double)(float)c.dx) && is_pow2(2.0 * (double)(float)c.dy)));
         if (want == WSB_KERNEL_AUTO)
             want = tma_ok ? WSB_KERNEL_STEP_FUSED_TMA : reg_ok ? WSB_KERNEL_STEP_FUSED_REG : WSB_KERNEL_STAGE_DIRECT;
         if (want == WSB_KERNEL_STEP_FUSED_REG || want == WSB_KERNEL_STEP_FUSED_TMA) {
@@ -1326,7 +1353,7 @@ static int step_host_pipelined(wsb_sim *s, const void *const in[3], void *const 
         }
     }
     const Geometry<T> geo = g->geom<T>();
-    const Physics<T> ph = g->physics<T>(s->cfg.gravity, s->cfg.coriolis_f);
+    const Physics<T> ph = sim_physics<T>(s);
     void *cur3[3] = {g->f[0].base, g->f[1].base, g->f[2].base};
     StepArgs<T> a = step_args<T>(s);
     // 16 slabs: the call ends one slab after the last upload ((1 + 1/n) x the transfer) and every slab costs about

@@ -159,7 +159,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <typename T, int NST, int V, bool RECIP, bool CL, bool FOLD>
+template <typename T, int NST, int V, bool RECIP, bool CL, bool FOLD, bool EXT>
 struct SweepT {
     using L = Layout<T, NST, V>;
     using Windows = Row<T, V>[(NST > 1 ? NST - 1 : 1)][3];
@@ -174,6 +174,7 @@ struct SweepT {
     const StepArgs<T> &a;
     PhysicsF2 ph2;    // splatted constants of the packed path
     PhysicsFold phf;  // ... of its folded variant (wsb_arith.cuh)
+    PhysicsExtF2 phe; // ... of the extended physics (EXT)
     float rs;         // FOLD: r = 1/(2dx), folded into every stage coefficient; else unused
     const CUtensorMap *tm_u, *tm_v, *tm_h;  // tiled-TMA descriptors of the y_n planes (kernel parameters)
     int lane, c0, xs;
@@ -283,8 +284,11 @@ struct SweepT {
         }
     }
 
+    // r: local index of the centre row (EXT: the beta plane needs the global one)
     __device__ __forceinline__ void tendency_row(const Row<T, V> &U, const Row<T, V> &C, const Row<T, V> &D,
-                                                 Row<T, V> &k) const {
+                                                 Row<T, V> &k, int r) const {
+        T fy = T(0);
+        if constexpr (EXT) fy = ext_coriolis<T>(ph, r + g.row0);
         T Lft[3], Rgt[3];
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
@@ -303,7 +307,10 @@ struct SweepT {
                     rg[f] = (p == V / 2 - 1) ? (float)Rgt[f] : (float)C.f[f][2 * p + 2];
                 }
                 F2 du, dv, dh;
-                if constexpr (FOLD)
+                if constexpr (EXT)
+                    tendency_pair_ext(ph2, phe, (float)fy, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]),
+                                      lf[1], rg[1], P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
+                else if constexpr (FOLD)
                     tendency_pair_folded(phf, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1],
                                          rg[1], P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
                 else
@@ -320,6 +327,11 @@ struct SweepT {
             const T uL = (e == 0) ? Lft[0] : C.f[0][e - 1], uR = (e == V - 1) ? Rgt[0] : C.f[0][e + 1];
             const T vL = (e == 0) ? Lft[1] : C.f[1][e - 1], vR = (e == V - 1) ? Rgt[1] : C.f[1][e + 1];
             const T hL = (e == 0) ? Lft[2] : C.f[2][e - 1], hR = (e == V - 1) ? Rgt[2] : C.f[2][e + 1];
+            if constexpr (EXT)
+                tendency_cell_ext<T, RECIP>(ph, fy, C.f[0][e], C.f[1][e], C.f[2][e], uL, uR, U.f[0][e], D.f[0][e], vL, vR,
+                                            U.f[1][e], D.f[1][e], hL, hR, U.f[2][e], D.f[2][e], k.f[0][e], k.f[1][e],
+                                            k.f[2][e]);
+            else
             tendency_cell<T, RECIP>(ph, C.f[0][e], C.f[1][e], C.f[2][e], uL, uR, U.f[0][e], D.f[0][e], vL, vR,
                                     U.f[1][e], D.f[1][e], hL, hR, U.f[2][e], D.f[2][e], k.f[0][e], k.f[1][e],
                                     k.f[2][e]);
@@ -403,16 +415,16 @@ struct SweepT {
             if constexpr (kYwin) {
                 ld_y<PH, 0>(Yw[PH], G);
                 yb = Yw[(PH + 2) % 3];
-                tendency_row(Yw[(PH + 1) % 3], yb, Yw[PH], k);
+                tendency_row(Yw[(PH + 1) % 3], yb, Yw[PH], k, r);
             } else {
                 Row<T, V> U, D;
                 ld_y<PH, 2>(U, G);
                 ld_y<PH, 1>(yb, G);
                 ld_y<PH, 0>(D, G);
-                tendency_row(U, yb, D, k);
+                tendency_row(U, yb, D, k, r);
             }
         } else {
-            tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k);
+            tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k, r);
             if constexpr (kYwin && S1 == 2) yb = Yw[(PH + 1) % 3];
             else ld_y<PH, S1>(yb, G);
         }
@@ -644,7 +656,7 @@ __device__ __forceinline__ void peer_signal(unsigned *flag) {
     if (threadIdx.x == 0) atomicAdd_system(flag, 1u);
 }
 
-template <typename T, int NST, int V, bool RECIP, int MINB, bool CL, bool FOLD>
+template <typename T, int NST, int V, bool RECIP, int MINB, bool CL, bool FOLD, bool EXT>
 __global__ void __launch_bounds__(32, MINB)
     step_tma_kernel(const Geometry<T> g, const Physics<T> ph, const StepArgs<T> a, const int rows_per_chunk,
                     const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
@@ -674,10 +686,11 @@ __global__ void __launch_bounds__(32, MINB)
     if ((peer_up || peer_dn) && a.px.target)
         peer_wait(a.px.wait + (peer_dn ? 1 : 0), a.px.target * gridDim.x * gridDim.z, a.ovl_err);
 
-    SweepT<T, NST, V, RECIP, CL, FOLD> sw(g, ph, a);
+    SweepT<T, NST, V, RECIP, CL, FOLD, EXT> sw(g, ph, a);
     if constexpr (std::is_same<T, float>::value) {
         sw.ph2 = physics_f2(ph);
         sw.phf = physics_fold(ph);
+        sw.phe = physics_ext_f2(ph);
         sw.rs = ph.rdx;
     }
     sw.tm_u = &tm_u;
@@ -804,6 +817,10 @@ cudaError_t make_plane_map(CUtensorMap *map, const Geometry<T> &g, const T *orig
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// the extended-physics kernels exist for the default cells-per-lane choice of each (type, stage count)
+template <typename T, int NST, int V>
+constexpr bool kExtInstantiated = std::is_same<T, float>::value ? (NST == 2 ? V == 4 : V == 2) : (NST == 4 ? V == 1 : V == 2);
+
 template <typename T, int NST, int V, int MINB>
 cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepArgs<T> &a, cudaStream_t st) {
     using L = Layout<T, NST, V>;
@@ -837,18 +854,31 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
         cfg.dynamicSmemBytes = smem;
         return cudaLaunchKernelEx(&cfg, kernel, g, ph, aa, rpc, tu, tv, th);
     };
+    if (ph.ext) {
+        // extended physics (beta plane, viscosity, diffusivity): power-of-two spacing only on this path (the per-stage
+        // path takes any spacing); instantiated for the default strip widths
+        if constexpr (kExtInstantiated<T, NST, V>) {
+            if (!ph.recip) return cudaErrorNotSupported;
+            if constexpr (NST == 4) {
+                if (a.classical) return launch(step_tma_kernel<T, NST, V, true, MINB, true, false, true>, L::smem_bytes(true));
+            }
+            return launch(step_tma_kernel<T, NST, V, true, MINB, false, false, true>, L::smem_bytes(false));
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
     if constexpr (NST == 4) {
         if (a.classical)  // textbook RK4 opt-in: separate instantiation, one more 3-row ring in shared memory
-            return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, true, false>, L::smem_bytes(true))
-                            : launch(step_tma_kernel<T, NST, V, false, MINB, true, false>, L::smem_bytes(true));
+            return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, true, false, false>, L::smem_bytes(true))
+                            : launch(step_tma_kernel<T, NST, V, false, MINB, true, false, false>, L::smem_bytes(true));
     }
     if constexpr (std::is_same<T, float>::value && V % 2 == 0) {
         // folded arithmetic (opt-in): one spacing, exact reciprocal
         if (a.fold && ph.recip && ph.rdx == ph.rdy)
-            return launch(step_tma_kernel<T, NST, V, true, MINB, false, true>, L::smem_bytes(false));
+            return launch(step_tma_kernel<T, NST, V, true, MINB, false, true, false>, L::smem_bytes(false));
     }
-    return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, false, false>, L::smem_bytes(false))
-                    : launch(step_tma_kernel<T, NST, V, false, MINB, false, false>, L::smem_bytes(false));
+    return ph.recip ? launch(step_tma_kernel<T, NST, V, true, MINB, false, false, false>, L::smem_bytes(false))
+                    : launch(step_tma_kernel<T, NST, V, false, MINB, false, false, false>, L::smem_bytes(false));
 }
 
 }  // namespace

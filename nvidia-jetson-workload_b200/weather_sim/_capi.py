@@ -51,7 +51,11 @@ class wsb_config(ctypes.Structure):
         ("nranks", ctypes.c_int32),
         ("nccl_unique_id", ctypes.c_void_p),
         ("arith_mode", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 7),
+        ("physics_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 6),
+        ("beta", ctypes.c_double),
+        ("viscosity", ctypes.c_double),
+        ("diffusivity", ctypes.c_double),
     ]
 
 
@@ -350,7 +354,9 @@ class Simulation:
 
     def __init__(self, width, height, model="shallow_water", integrator="rk4", dx=1.0, dy=1.0, dt=0.01,
                  gravity=9.81, coriolis_f=0.0, max_time=10.0, dtype=np.float32, num_levels=1, device_id=0,
-                 rk4_classical=False, kernel="auto", rank=0, nranks=1, nccl_id=None, arith="strict"):
+                 rk4_classical=False, kernel="auto", rank=0, nranks=1, nccl_id=None, arith="strict", extended=None):
+        """extended=(beta, viscosity, diffusivity): the non-reference beta-plane / viscous tendencies
+        (WSB_PHYSICS_EXTENDED, include/weather_b200.h)."""
         self._lib = load_library()
         cfg = wsb_config()
         cfg.struct_size = ctypes.sizeof(wsb_config)
@@ -365,6 +371,9 @@ class Simulation:
         cfg.kernel_variant = KERNEL[kernel] if isinstance(kernel, str) else int(kernel)
         cfg.rank, cfg.nranks = rank, nranks
         cfg.arith_mode = ARITH[arith] if isinstance(arith, str) else int(arith)
+        if extended is not None:
+            cfg.physics_mode = 1
+            cfg.beta, cfg.viscosity, cfg.diffusivity = (float(x) for x in extended)
         self._id_buf = None
         if nranks > 1:
             self._id_buf = ctypes.create_string_buffer(bytes(nccl_id), NCCL_UNIQUE_ID_BYTES)

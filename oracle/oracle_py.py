@@ -70,6 +70,8 @@ def _load_oracle():
             getattr(lib, "wso_steps" + sfx).restype = ctypes.c_int
             getattr(lib, "wso_set_dt" + sfx).argtypes = [ctypes.c_void_p, ctypes.c_double]
             getattr(lib, "wso_set_dt" + sfx).restype = None
+            getattr(lib, "wso_set_extended" + sfx).argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3
+            getattr(lib, "wso_set_extended" + sfx).restype = None
             f = getattr(lib, "wso_tendencies" + sfx)
             f.restype = None
             f.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.c_void_p] * 6
@@ -128,7 +130,8 @@ class Oracle(_SimBase):
     """The C restatement. dtype np.float32 (reference arithmetic) or np.float64."""
 
     def __init__(self, width, height, model=0, integrator=2, dx=1.0, dy=1.0, dt=0.01, gravity=9.81,
-                 coriolis_f=0.0, dtype=np.float32, rk4_classical=False):
+                 coriolis_f=0.0, dtype=np.float32, rk4_classical=False, extended=None):
+        """extended=(beta, viscosity, diffusivity) switches on the non-reference beta-plane / viscous tendencies."""
         self.lib = _load_oracle()
         self.dtype = np.dtype(dtype)
         self.sfx = "_f32" if self.dtype == np.float32 else "_f64"
@@ -141,6 +144,9 @@ class Oracle(_SimBase):
                                                              gravity, coriolis_f, int(rk4_classical))
         if not self.h:
             raise ValueError("Grid dimensions must be positive")
+        if extended is not None:
+            ext = [float(np.float32(x)) if self.dtype == np.float32 else float(x) for x in extended]
+            getattr(self.lib, "wso_set_extended" + self.sfx)(self.h, *ext)
 
     def _f(self, name):
         return getattr(self.lib, name + self.sfx)

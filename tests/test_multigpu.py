@@ -123,6 +123,25 @@ def _worker(rank, world, port, cases, out_q):
                     if got[k][lev].tobytes() != o.get_field(k).tobytes():
                         msgs.append(f"primitive slabs level {lev} field {k} differs")
                 o.close()
+        # extended physics on slabs: the beta plane reads the GLOBAL row index, viscosity the ghost rows
+        W, H = 150, 97
+        u, v, h = syn.white_noise_state(W, H, seed=21)
+        ext = (0.02, 0.05, 0.03)
+        sim = wd.slab_simulation(W, H, rank, world, device_id=rank, integrator="rk4", rk4_classical=True, coriolis_f=0.1,
+                                 max_time=1e30, extended=ext)
+        r0, n = sim.local_rows
+        sim.set_state(u[r0:r0 + n], v[r0:r0 + n], h[r0:r0 + n])
+        sim.step(4)
+        got = {k: wd.gather_rows(sim.get_field(k), 0) for k in ("u", "v", "h")}
+        sim.close()
+        if rank == 0:
+            o = Oracle(W, H, 0, 2, coriolis_f=0.1, rk4_classical=True, extended=ext)
+            o.set_state(u, v, h)
+            o.step(4)
+            for k in got:
+                if got[k].tobytes() != o.get_field(k).tobytes():
+                    msgs.append(f"extended physics on slabs: field {k} differs")
+            o.close()
         # the drop-in surface on slabs: pyweather_sim.SimulationConfig.rank / nranks / nccl_unique_id
         import weather_sim.pyweather_sim as m
         W, H = 120, 90

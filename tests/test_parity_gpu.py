@@ -539,6 +539,63 @@ def test_folded_arithmetic_subnormal_bound():
     o.close()
 
 
+# ------------------------------------------------------------- extended physics (non-reference opt-in) --
+EXT = (0.02, 0.05, 0.03)  # beta, viscosity, diffusivity
+
+
+@pytest.mark.parametrize("kernel", ["stage_direct", "step_fused_tma"])
+@pytest.mark.parametrize("integ,classical", [(0, False), (1, False), (2, False), (2, True)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_extended_physics_vs_its_oracle(kernel, integ, classical, dtype):
+    """WSB_PHYSICS_EXTENDED (beta plane + viscosity + diffusivity: the barotropic model the reference advertises and
+    stubs) has no reference to be graded against; its specification is the oracle's restatement, and the kernels
+    follow it bit for bit -- per-stage and whole-step paths, ragged shapes, both precisions."""
+    for W, H, dx, dy in ((200, 210, 1.0, 1.0), (57, 131, 0.5, 2.0), (9, 6, 1.0, 1.0)):
+        u, v, h = (a.astype(dtype) for a in syn.random_vorticity(W, H, dtype=np.float64))
+        h = (h + syn.gaussian_bump(W, H, dtype=np.float64)[2] - 10.0).astype(dtype)
+        o = Oracle(W, H, 0, integ, coriolis_f=0.1, dx=dx, dy=dy, dtype=dtype, rk4_classical=classical, extended=EXT)
+        s = cuda_sim(W, H, 0, integ, kernel, coriolis_f=0.1, dx=dx, dy=dy, dtype=dtype, rk4_classical=classical,
+                     extended=EXT)
+        assert s.kernel_name == kernel
+        o.set_state(u, v, h)
+        s.set_state(u, v, h)
+        o.step(6)
+        s.step(6)
+        for n in ("u", "v", "h", "vorticity"):
+            assert_bit_equal(s.get_field(n), o.get_field(n), f"extended {kernel} {W}x{H} i{integ} cl{classical} {n}")
+        s.close()
+        o.close()
+
+
+def test_extended_physics_general_spacing_and_sanity():
+    ic = syn.random_vorticity(96, 64)
+    # any spacing: AUTO falls back to the per-stage kernel (exact three-operation division), still the oracle's bits
+    o = Oracle(96, 64, 0, 2, dx=0.8, dy=1.7, coriolis_f=0.1, rk4_classical=True, extended=EXT)
+    s = cuda_sim(96, 64, 0, 2, "auto", dx=0.8, dy=1.7, coriolis_f=0.1, rk4_classical=True, extended=EXT)
+    assert s.kernel_name == "stage_direct"
+    o.set_state(*ic)
+    s.set_state(*ic)
+    o.step(5)
+    s.step(5)
+    assert_bit_equal(s.get_field("h"), o.get_field("h"), "extended, general spacing")
+    s.close()
+    # all three parameters zero: numerically the reference tendencies (only the sign of a zero may differ)
+    s0 = cuda_sim(96, 64, 0, 2, "auto", coriolis_f=0.1, extended=(0.0, 0.0, 0.0))
+    s1 = cuda_sim(96, 64, 0, 2, "auto", coriolis_f=0.1)
+    for x in (s0, s1):
+        x.set_state(*ic)
+        x.step(5)
+    assert np.array_equal(s0.get_field("u"), s1.get_field("u")) and np.array_equal(s0.get_field("h"), s1.get_field("h"))
+    # viscosity removes kinetic energy: the viscous run ends with less of it than the inviscid one
+    sv = cuda_sim(96, 64, 0, 2, "auto", coriolis_f=0.1, extended=(0.0, 0.5, 0.0))
+    sv.set_state(*ic)
+    sv.step(5)
+    ke = lambda x: float(np.sum(x.get_field("u").astype(np.float64) ** 2 + x.get_field("v").astype(np.float64) ** 2))  # noqa: E731
+    assert ke(sv) < ke(s1)
+    for x in (s0, s1, sv):
+        x.close()
+
+
 @pytest.mark.parametrize("kernel", VARIANTS)
 def test_subnormal_and_extreme_magnitudes(kernel):
     """No flush-to-zero anywhere (scalar and packed fp32x2 paths): fields in the subnormal range, mixed with
