@@ -55,13 +55,43 @@ struct FastDiv<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 };
 template <typename T>
+__device__ __forceinline__ T div_fast(T x, T d, T r) {
+    const T q = Ar<T>::mul(x, r);
+    const T e = FastDiv<T>::fma(-q, d, x);
+    return FastDiv<T>::fma(e, r, q);
+}
+template <typename T>
 __device__ __forceinline__ T div_by_invariant(T x, T d, T r) {
-    if (r != T(0) && FastDiv<T>::ordinary(x)) {  // r == 0: the host found d outside the window where this is proven
-        const T q = Ar<T>::mul(x, r);
-        const T e = FastDiv<T>::fma(-q, d, x);
-        return FastDiv<T>::fma(e, r, q);
+    // r == 0: the host found d outside the window where the sequence is proven
+    return (r != T(0) && FastDiv<T>::ordinary(x)) ? div_fast<T>(x, d, r) : Ar<T>::div(x, d);
+}
+// The six centred differences of a cell divided at once. The IEEE divisions live in ONE out-of-line function per
+// type: inlined at every site (six per cell and stage, hundreds per unrolled whole-step kernel) their ~30
+// instructions plus slow-path call made the true-division kernels 17 k instructions long and instruction-fetch
+// bound (3.1 ms per 8192^2 RK4 step); a cell takes the call only if one of its six operands is not ordinary.
+template <typename T>
+struct Six {
+    T q[6];
+};
+template <typename T>
+__device__ __noinline__ Six<T> ieee_div6(T a0, T a1, T a2, T a3, T a4, T a5, T ddx, T ddy) {
+    Six<T> r;
+    r.q[0] = Ar<T>::div(a0, ddx); r.q[1] = Ar<T>::div(a1, ddy); r.q[2] = Ar<T>::div(a2, ddx);
+    r.q[3] = Ar<T>::div(a3, ddy); r.q[4] = Ar<T>::div(a4, ddx); r.q[5] = Ar<T>::div(a5, ddy);
+    return r;
+}
+// x: the differences (ux, uy, vx, vy, hx, hy order: dx, dy, dx, dy, dx, dy)
+template <typename T>
+__device__ __forceinline__ Six<T> div6_by_invariant(const T (&x)[6], const Physics<T> &ph) {
+    Six<T> r;
+    bool ok = ph.rdx != T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        ok = ok && FastDiv<T>::ordinary(x[k]);
+        r.q[k] = div_fast<T>(x[k], (k & 1) ? ph.ddy : ph.ddx, (k & 1) ? ph.rdy : ph.rdx);
     }
-    return Ar<T>::div(x, d);
+    if (!ok) r = ieee_div6<T>(x[0], x[1], x[2], x[3], x[4], x[5], ph.ddx, ph.ddy);
+    return r;
 }
 
 // (hi - lo) / (2*d): true IEEE division (by the exact three-operation sequence above), or the bit-identical multiply
@@ -73,6 +103,22 @@ __device__ __forceinline__ T cdiff(T hi, T lo, T dd, T rd) {
     else return div_by_invariant<T>(d, dd, rd);
 }
 
+// the six centred differences of weather_simulation.cpp:521-528
+template <typename T, bool RECIP>
+__device__ __forceinline__ void centred_differences(const Physics<T> &ph, T uL, T uR, T uU, T uD, T vL, T vR, T vU, T vD,
+                                                    T hL, T hR, T hU, T hD, T &ux, T &uy, T &vx, T &vy, T &hx, T &hy) {
+    using A = Ar<T>;
+    if constexpr (RECIP) {
+        ux = A::mul(A::sub(uR, uL), ph.rdx); uy = A::mul(A::sub(uD, uU), ph.rdy);
+        vx = A::mul(A::sub(vR, vL), ph.rdx); vy = A::mul(A::sub(vD, vU), ph.rdy);
+        hx = A::mul(A::sub(hR, hL), ph.rdx); hy = A::mul(A::sub(hD, hU), ph.rdy);
+    } else {
+        const T d[6] = {A::sub(uR, uL), A::sub(uD, uU), A::sub(vR, vL), A::sub(vD, vU), A::sub(hR, hL), A::sub(hD, hU)};
+        const Six<T> q = div6_by_invariant<T>(d, ph);
+        ux = q.q[0]; uy = q.q[1]; vx = q.q[2]; vy = q.q[3]; hx = q.q[4]; hy = q.q[5];
+    }
+}
+
 // weather_simulation.cpp:516-537 for one cell. L/R/U/D are the clamped neighbours (:510-513).
 //   du = ((((-u)*ux) - (v*uy)) - (g*hx)) + (f*v)
 //   dv = ((((-u)*vx) - (v*vy)) - (g*hy)) - (f*u)
@@ -81,12 +127,8 @@ template <typename T, bool RECIP>
 __device__ __forceinline__ void tendency_cell(const Physics<T> &ph, T u, T v, T h, T uL, T uR, T uU, T uD, T vL,
                                               T vR, T vU, T vD, T hL, T hR, T hU, T hD, T &du, T &dv, T &dh) {
     using A = Ar<T>;
-    const T ux = cdiff<T, RECIP>(uR, uL, ph.ddx, ph.rdx);
-    const T uy = cdiff<T, RECIP>(uD, uU, ph.ddy, ph.rdy);
-    const T vx = cdiff<T, RECIP>(vR, vL, ph.ddx, ph.rdx);
-    const T vy = cdiff<T, RECIP>(vD, vU, ph.ddy, ph.rdy);
-    const T hx = cdiff<T, RECIP>(hR, hL, ph.ddx, ph.rdx);
-    const T hy = cdiff<T, RECIP>(hD, hU, ph.ddy, ph.rdy);
+    T ux, uy, vx, vy, hx, hy;
+    centred_differences<T, RECIP>(ph, uL, uR, uU, uD, vL, vR, vU, vD, hL, hR, hU, hD, ux, uy, vx, vy, hx, hy);
     du = A::add(A::sub(A::sub(A::mul(-u, ux), A::mul(v, uy)), A::mul(ph.g, hx)), A::mul(ph.f, v));
     dv = A::sub(A::sub(A::sub(A::mul(-u, vx), A::mul(v, vy)), A::mul(ph.g, hy)), A::mul(ph.f, u));
     dh = A::sub(A::sub(A::mul(-h, A::add(ux, vy)), A::mul(u, hx)), A::mul(v, hy));
@@ -110,12 +152,8 @@ template <typename T, bool RECIP>
 __device__ __forceinline__ void tendency_cell_ext(const Physics<T> &ph, T fy, T u, T v, T h, T uL, T uR, T uU, T uD,
                                                   T vL, T vR, T vU, T vD, T hL, T hR, T hU, T hD, T &du, T &dv, T &dh) {
     using A = Ar<T>;
-    const T ux = cdiff<T, RECIP>(uR, uL, ph.ddx, ph.rdx);
-    const T uy = cdiff<T, RECIP>(uD, uU, ph.ddy, ph.rdy);
-    const T vx = cdiff<T, RECIP>(vR, vL, ph.ddx, ph.rdx);
-    const T vy = cdiff<T, RECIP>(vD, vU, ph.ddy, ph.rdy);
-    const T hx = cdiff<T, RECIP>(hR, hL, ph.ddx, ph.rdx);
-    const T hy = cdiff<T, RECIP>(hD, hU, ph.ddy, ph.rdy);
+    T ux, uy, vx, vy, hx, hy;
+    centred_differences<T, RECIP>(ph, uL, uR, uU, uD, vL, vR, vU, vD, hL, hR, hU, hD, ux, uy, vx, vy, hx, hy);
     const T a = A::add(A::sub(A::sub(A::mul(-u, ux), A::mul(v, uy)), A::mul(ph.g, hx)), A::mul(fy, v));
     const T b = A::sub(A::sub(A::sub(A::mul(-u, vx), A::mul(v, vy)), A::mul(ph.g, hy)), A::mul(fy, u));
     const T c = A::sub(A::sub(A::mul(-h, A::add(ux, vy)), A::mul(u, hx)), A::mul(v, hy));

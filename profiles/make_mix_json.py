@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """profiles/instruction_mix.json and the traffic stamp from ncu captures of the RK4 whole-step kernel.
 
-usage: python profiles/make_mix_json.py <strict.ncu-rep> [<folded.ncu-rep>]   (captures taken with --import-source on)
+usage: [WSB_MIX_RPC=256] python profiles/make_mix_json.py <strict.ncu-rep> [<folded.ncu-rep>]
+       (captures taken with --import-source on; WSB_MIX_RPC = rows per chunk of the captured launches)
 
 For each capture: executed warp instructions per opcode (ncu source page), divided by the strip-row iterations of
 the launch (strips x chunks x (rows_per_chunk + 8)), and the FMA-pipe cycles per iteration they stand for (scalar
@@ -22,7 +23,8 @@ sys.path.insert(0, ROOT)
 from bench import source_stamp  # noqa: E402
 
 W = H = 8192
-COLS, RPC = 56, 64
+COLS = 56
+RPC = int(os.environ.get("WSB_MIX_RPC", "256"))  # rows per chunk of the captured launch (the shipped default at 8192^2)
 ITER = -(-W // COLS) * -(-H // RPC) * (RPC + 8)
 
 
