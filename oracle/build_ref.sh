@@ -7,7 +7,8 @@
 # it from there, and leaves only binaries in oracle/_ref/:
 #   oracle/_ref/libws_ref.so            reference classes behind oracle/ref_shim.cpp (ctypes)
 #   oracle/_ref/pyweather_sim.*.so      the reference's own pybind11 module (surface checks)
-#   oracle/_ref/weather_simulation.pyc  the reference's own Python wrapper, byte-compiled unmodified
+#   oracle/_ref/weather_simulation.pyc.bin  the reference's own Python wrapper, byte-compiled unmodified (the
+#                                        ".bin" keeps snapshot tools that drop *.pyc from losing it)
 #
 # The six patches are mechanical compile fixes; none
 # touches arithmetic. -ffp-contract=off is mandatory (GCC defaults to "fast").
@@ -27,7 +28,7 @@ if [ ! -d "$REF" ]; then
 fi
 
 EXT_SUFFIX="$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')"
-if [ "${1:-}" != "--force" ] && [ -f "$OUT/libws_ref.so" ] && [ -f "$OUT/pyweather_sim$EXT_SUFFIX" ] && [ -f "$OUT/weather_simulation.pyc" ] \
+if [ "${1:-}" != "--force" ] && [ -f "$OUT/libws_ref.so" ] && [ -f "$OUT/pyweather_sim$EXT_SUFFIX" ] && [ -f "$OUT/weather_simulation.pyc.bin" ] \
    && [ "$OUT/libws_ref.so" -nt "$HERE/ref_shim.cpp" ] && [ "$OUT/libws_ref.so" -nt "$HERE/build_ref.sh" ]; then
     exit 0
 fi
@@ -69,8 +70,8 @@ wait $PID2
 # The reference's own Python wrapper (python/weather_simulation.py), UNMODIFIED, byte-compiled: a binary artefact
 # like the two libraries above (no reference source enters the repo). tests/test_reference_wrapper.py puts it next
 # to the B200 pyweather_sim module and next to the reference's, and runs the same user script on both.
-"$PY" - "$REF/../python/weather_simulation.py" "$OUT/weather_simulation.pyc" <<'PYEOF'
+"$PY" - "$REF/../python/weather_simulation.py" "$OUT/weather_simulation.pyc.bin" <<'PYEOF'
 import py_compile, sys
 py_compile.compile(sys.argv[1], cfile=sys.argv[2], dfile="reference:src/weather-sim/python/weather_simulation.py", doraise=True)
 PYEOF
-echo "build_ref: wrote $OUT/libws_ref.so, $OUT/pyweather_sim$EXT_SUFFIX and $OUT/weather_simulation.pyc"
+echo "build_ref: wrote $OUT/libws_ref.so, $OUT/pyweather_sim$EXT_SUFFIX and $OUT/weather_simulation.pyc.bin"

@@ -1,5 +1,5 @@
 """The reference's OWN Python wrapper (src/weather-sim/python/weather_simulation.py, unmodified, byte-compiled by
-oracle/build_ref.sh into oracle/_ref/weather_simulation.pyc) imported on top of the B200 `pyweather_sim` module --
+oracle/build_ref.sh into oracle/_ref/weather_simulation.pyc.bin) imported on top of the B200 `pyweather_sim` module --
 the drop-in claim of SURVEY.md section 7 step 3 / section 8b: `from .pyweather_sim import (...)` at
 weather_simulation.py:16-29 must find every name, and `WeatherSimulationWrapper` (:194-371) must drive the GPU path.
 
@@ -18,7 +18,7 @@ import textwrap
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PYC = os.path.join(ROOT, "oracle", "_ref", "weather_simulation.pyc")
+PYC = os.path.join(ROOT, "oracle", "_ref", "weather_simulation.pyc.bin")
 OURS = glob.glob(os.path.join(ROOT, "nvidia-jetson-workload_b200", "weather_sim", "pyweather_sim*.so"))
 REFS = glob.glob(os.path.join(ROOT, "oracle", "_ref", "pyweather_sim*.so"))
 
@@ -97,7 +97,7 @@ def _run(tmp_path, module_so, backend, script):
 
 
 needs_artifacts = pytest.mark.skipif(not (os.path.exists(PYC) and OURS),
-                                     reason="oracle/_ref/weather_simulation.pyc or the pyweather_sim shim not built")
+                                     reason="oracle/_ref/weather_simulation.pyc.bin or the pyweather_sim shim not built")
 
 
 @needs_artifacts
