@@ -98,7 +98,10 @@ typedef enum wsb_physics_mode {
                                   primitive-variable form -- shallow-water tendencies on a beta plane
                                   f(y) = coriolis_f + beta*dy*(y - (H-1)/2), eddy viscosity on u, v and
                                   diffusivity on h (5-point Laplacian, same clamped neighbours). Applies to
-                                  every model and integrator; power-of-two spacing on the whole-step kernels. */
+                                  every model and integrator; power-of-two spacing on the whole-step kernels.
+                                  On WSB_MODEL_PRIMITIVE_EQUATIONS it also replaces the constant T/p drift by
+                                  transport of p, T, q with the level's flow (advection + diffusivity; per-stage
+                                  kernels, one rank). */
 } wsb_physics_mode;
 
 /* Which hand-written sm_100a path advances the state. All variants produce bit-identical results. */

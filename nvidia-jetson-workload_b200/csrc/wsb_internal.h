@@ -108,6 +108,18 @@ struct PeerExchange {
     unsigned target;            // fused steps so far (flags count strips x levels per step)
 };
 
+// One RK stage of the tracer transport of the extended Primitive model (p, T, q carried by the stage's flow):
+// O = Y + c * (-u*c_x - v*c_y + kappa*lap(c)) for each of the three tracers; u, v and the tracers C of the stage's
+// input state (oracle/ws_oracle_body.inc, tracer_tendencies).
+template <typename T>
+struct TracerArgs {
+    const T *u, *v;   // velocity of the stage's input state
+    const T *C[3];    // tracers of the stage's input state (p, T, q)
+    const T *Y[3];    // base state
+    T *O[3];          // output state
+    T c;              // stage coefficient, already rounded: dt or (0.5f*dt)
+};
+
 // Whole-step fused kernel arguments (all RK stages in one pass over the grid).
 template <typename T>
 struct StepArgs {
@@ -139,6 +151,9 @@ cudaError_t launch_stage_direct(const Geometry<T> &g, const Physics<T> &ph, cons
 template <typename T>
 cudaError_t launch_diagnostics(const Geometry<T> &g, const Physics<T> &ph, const T *u, const T *v, T *vort,
                                T *div, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_tracer_stage(const Geometry<T> &g, const Physics<T> &ph, const TracerArgs<T> &a, cudaStream_t st);
 
 // O = Y + c*k for a constant k (the Primitive-equations T/p "tendencies", weather_simulation.cpp:201-214)
 template <typename T>

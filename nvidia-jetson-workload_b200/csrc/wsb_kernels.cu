@@ -58,6 +58,32 @@ __global__ void __launch_bounds__(kBX *kBY)
     }
 }
 
+// Tracer transport of the extended Primitive model: one cell per thread, the three tracers share the cell's u, v and
+// neighbour indices. Operation order: oracle/ws_oracle_body.inc (tracer_tendencies) -- (-u*c_x - v*c_y) + kappa*lap.
+template <typename T, bool RECIP>
+__global__ void __launch_bounds__(kBX *kBY)
+    tracer_stage_kernel(const Geometry<T> g, const Physics<T> ph, const TracerArgs<T> a) {
+    using A = Ar<T>;
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const long long i = (long long)blockIdx.z * g.level_stride + (long long)y * g.pitch + x;
+    const int gy = g.row0 + y;
+    const long long iL = (x > 0) ? i - 1 : i, iR = (x < g.W - 1) ? i + 1 : i;
+    const long long iU = (gy > 0) ? i - g.pitch : i, iD = (gy < g.Hglobal - 1) ? i + g.pitch : i;
+    const T u = a.u[i], v = a.v[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T *c = a.C[k];
+        const T cc = c[i], cL = c[iL], cR = c[iR], cU = c[iU], cD = c[iD];
+        const T cx = cdiff<T, RECIP>(cR, cL, ph.ddx, ph.rdx);
+        const T cy = cdiff<T, RECIP>(cD, cU, ph.ddy, ph.rdy);
+        const T adv = A::sub(A::mul(-u, cx), A::mul(v, cy));
+        const T dc = A::add(adv, A::mul(ph.kappa, ext_laplacian<T>(ph, cc, cL, cR, cU, cD)));
+        a.O[k][i] = axpy<T>(a.Y[k][i], a.c, dc);
+    }
+}
+
 // Vorticity and divergence (weather_grid.cpp:96-100 and :114-118) as a row sweep: a thread owns 16 bytes of a row
 // (4 floats / 2 doubles), walks down kDiagRows rows with u and v in 3-row register windows (every element is read
 // once per chunk: 16 B/cell fp32 of traffic instead of eight scattered loads), takes horizontal neighbours from
@@ -289,6 +315,13 @@ __global__ void __launch_bounds__(kBX *kBY)
 }
 
 template <typename T>
+cudaError_t launch_tracer_stage(const Geometry<T> &g, const Physics<T> &ph, const TracerArgs<T> &a, cudaStream_t st) {
+    if (ph.recip) tracer_stage_kernel<T, true><<<grid_for(g, g.H, g.W), dim3(kBX, kBY), 0, st>>>(g, ph, a);
+    else tracer_stage_kernel<T, false><<<grid_for(g, g.H, g.W), dim3(kBX, kBY), 0, st>>>(g, ph, a);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_expand_separable(const Geometry<T> &g, T *p, const float *rowv, const float *colv, cudaStream_t st) {
     expand_separable_kernel<T><<<grid_for(g, g.H, g.W), dim3(kBX, kBY), 0, st>>>(g, p, rowv, colv);
     return cudaGetLastError();
@@ -317,6 +350,8 @@ cudaError_t launch_mass_energy(const Geometry<T> &g, const T *u, const T *v, con
     template cudaError_t launch_axpy_const2<T>(const Geometry<T> &, const T *, T *, const T *, T *, T, T, T,         \
                                                cudaStream_t);                                                       \
     template cudaError_t launch_fill<T>(const Geometry<T> &, T *, T, bool, cudaStream_t);                            \
+    template cudaError_t launch_tracer_stage<T>(const Geometry<T> &, const Physics<T> &, const TracerArgs<T> &,       \
+                                                cudaStream_t);                                                       \
     template cudaError_t launch_expand_separable<T>(const Geometry<T> &, T *, const float *, const float *,          \
                                                     cudaStream_t);                                                   \
     template cudaError_t launch_mass_energy<T>(const Geometry<T> &, const T *, const T *, const T *, double,         \

@@ -263,6 +263,7 @@ struct wsb_sim {
     // the reference swaps whole grids (weather_simulation.cpp:217): p/T/q of the "next" grid become current
     FieldBuf alt[WSB_NUM_FIELDS];
     void *next[3] = {nullptr, nullptr, nullptr};   // y_{n+1} planes
+    void *trA[3] = {nullptr, nullptr, nullptr};    // midpoint p, T, q of the extended Primitive model (RK2)
     void *tA[3] = {nullptr, nullptr, nullptr};     // stage scratch (per-stage paths)
     void *tB[3] = {nullptr, nullptr, nullptr};
     void *k1[3] = {nullptr, nullptr, nullptr};
@@ -340,6 +341,12 @@ static int effective_stages(const wsb_config &c) {
             return c.model == WSB_MODEL_SHALLOW_WATER ? 4 : 2;  // weather_simulation.cpp:334-338
         default: return 1;  // Euler, AdamsBashforth, SemiImplicit (:457-471)
     }
+}
+
+// extended physics on the PrimitiveEquations model: p, T, q are transported by the flow (tracer_stage_kernel)
+// instead of drifting by the reference's constants
+static inline bool prim_ext(const wsb_sim *s) {
+    return s->cfg.physics_mode == WSB_PHYSICS_EXTENDED && s->cfg.model == WSB_MODEL_PRIMITIVE_EQUATIONS;
 }
 
 // Physics of one tendency evaluation for this simulation: the grid's spacing + the configuration's constants
@@ -422,14 +429,42 @@ static int enqueue_step_stages(wsb_sim *s) {
     a.KA = a.KB = a.K1 = null_planes<const T>();
     a.dt6 = dt6;
     a.final_stage = 0;
+    // extended Primitive model: one tracer stage (p, T, q) beside every (u, v, h) stage, carried by that stage's
+    // input velocity; Primitive runs Euler or RK2 only (RK4 -> RK2, :334-338)
+    const int tf[3] = {WSB_FIELD_PRESSURE, WSB_FIELD_TEMPERATURE, WSB_FIELD_HUMIDITY};
+    auto tracer_stage = [&](const Planes3<const T> &S, void *const Cin[3], void *const Out[3], T c) -> int {
+        TracerArgs<T> t{};
+        t.u = S.u; t.v = S.v; t.c = c;
+        for (int k = 0; k < 3; ++k) {
+            t.C[k] = (const T *)plane_origin(s, Cin[k]);
+            t.Y[k] = (const T *)s->cur.origin(tf[k]);
+            t.O[k] = (T *)plane_origin(s, Out[k]);
+        }
+        WSB_CUDA(launch_tracer_stage<T>(s->cur.geom<T>(), sim_physics<T>(s), t, s->stream));
+        s->metrics.kernel_launches += 1;
+        return WSB_OK;
+    };
+    void *tr_cur[3] = {nullptr, nullptr, nullptr}, *tr_next[3] = {nullptr, nullptr, nullptr};
+    if (prim_ext(s)) {
+        for (int k = 0; k < 3; ++k) {
+            WSB_TRY(grid_materialize(&s->cur, tf[k]));
+            if (!s->alt[tf[k]].base) WSB_TRY(grid_alloc_plane(&s->cur, &s->alt[tf[k]].base));
+            if (s->nstages == 2 && !s->trA[k]) WSB_TRY(grid_alloc_plane(&s->cur, &s->trA[k]));
+            tr_cur[k] = s->cur.f[tf[k]].base;
+            tr_next[k] = s->alt[tf[k]].base;
+        }
+    }
     if (s->nstages == 1) {  // weather_simulation.cpp:160-218
         a.S = Y; a.O = planes<T>(s, s->next); a.c = dt;
         WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
+        if (prim_ext(s)) WSB_TRY(tracer_stage(Y, tr_cur, tr_next, dt));
     } else if (s->nstages == 2) {  // :220-323
         a.S = Y; a.O = planes<T>(s, s->tA); a.c = half_dt;
         WSB_TRY(enqueue_stage<T>(s, a, s->tA, true));
+        if (prim_ext(s)) WSB_TRY(tracer_stage(Y, tr_cur, s->trA, half_dt));
         a.S = planes<const T>(s, s->tA); a.O = planes<T>(s, s->next); a.c = dt;
         WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
+        if (prim_ext(s)) WSB_TRY(tracer_stage(planes<const T>(s, s->tA), s->trA, tr_next, dt));
     } else {  // :325-455
         const bool classical = s->cfg.rk4_mode == WSB_RK4_CLASSICAL;
         a.S = Y; a.O = planes<T>(s, s->tA); a.c = half_dt;
@@ -628,7 +663,7 @@ static int sim_enqueue_step(wsb_sim *s, bool follows_step = false) {
         if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_stages<double>(s));
         else WSB_TRY(enqueue_step_stages<float>(s));
     }
-    if (s->cfg.model == WSB_MODEL_PRIMITIVE_EQUATIONS) {
+    if (s->cfg.model == WSB_MODEL_PRIMITIVE_EQUATIONS && !prim_ext(s)) {
         if (s->dtype == WSB_F64) WSB_TRY(enqueue_primitive_tp<double>(s));
         else WSB_TRY(enqueue_primitive_tp<float>(s));
     }
@@ -1092,6 +1127,7 @@ static void sim_free(wsb_sim *s) {
     }
     if (s->xflags) cudaFree(s->xflags);
     if (s->comm) halo_comm_destroy(s->comm);
+    sim_free3(s->trA);
     sim_free3(s->next); sim_free3(s->tA); sim_free3(s->tB); sim_free3(s->k1); sim_free3(s->k2); sim_free3(s->k3);
     for (int k = 0; k < WSB_NUM_FIELDS; ++k)
         if (s->alt[k].base) cudaFree(s->alt[k].base);
@@ -1189,8 +1225,14 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         const bool classical4 = s->nstages == 4 && c.rk4_mode == WSB_RK4_CLASSICAL;
         // extended physics: whole-step TMA kernel on power-of-two spacing, else the per-stage kernel (any spacing)
         const bool ext = c.physics_mode == WSB_PHYSICS_EXTENDED;
+        // (the extended Primitive model needs the midpoint velocity in HBM for its tracer stage: per-stage kernels)
+        const bool pext = ext && c.model == WSB_MODEL_PRIMITIVE_EQUATIONS;
+        if (pext && c.nranks > 1) {
+            st = fail(WSB_ERR_INVALID_ARGUMENT, "extended physics on the PrimitiveEquations model runs on one rank");
+            break;
+        }
         const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4 && !ext;
-        const bool tma_ok = step_tma_supported(s->nstages, s->dtype) &&  // incl. the classical RK4 opt-in
+        const bool tma_ok = step_tma_supported(s->nstages, s->dtype) && !pext &&  // incl. the classical RK4 opt-in
                             (!ext || (is_pow2(2.0 * (double)(float)c.dx) && is_pow2(2.0 * (double)(float)c.dy)));
         if (want == WSB_KERNEL_AUTO)
             want = tma_ok ? WSB_KERNEL_STEP_FUSED_TMA : reg_ok ? WSB_KERNEL_STEP_FUSED_REG : WSB_KERNEL_STAGE_DIRECT;

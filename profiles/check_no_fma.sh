@@ -11,7 +11,7 @@ LIB="${1:-$(dirname "$0")/../nvidia-jetson-workload_b200/lib/libweather_b200.so}
 cuobjdump -sass "$LIB" | awk '
 /Function :/ {
     fn = $3
-    recip = (fn ~ /step_(tma|fused)_kernelI[fd]Li[0-9]+ELi[0-9]+ELb1/) || (fn ~ /(stage_direct|diagnostics)_kernelI[fd]Lb1/)
+    recip = (fn ~ /step_(tma|fused)_kernelI[fd]Li[0-9]+ELi[0-9]+ELb1/) || (fn ~ /(stage_direct|diagnostics|tracer_stage)_kernelI[fd]Lb1/)
     folded = (fn ~ /step_tma_kernelIfLi[0-9]+ELi[0-9]+ELb1ELi[0-9]+ELb0ELb1E/)
     if (recip) checked++
 }

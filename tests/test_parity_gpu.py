@@ -567,6 +567,38 @@ def test_extended_physics_vs_its_oracle(kernel, integ, classical, dtype):
         o.close()
 
 
+@pytest.mark.parametrize("integ", [0, 1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_extended_primitive_tracers_vs_its_oracle(integ, dtype):
+    """Extended physics on the PrimitiveEquations model: p, T and q are transported by the level's flow (advection +
+    diffusivity) instead of drifting by the reference's constants. Oracle restatement = specification; two levels,
+    each compared with the 2-D oracle of that level; power-of-two and general spacing (RK4 requested -> RK2, as ever)."""
+    W, H, L = 120, 70, 2
+    rng = np.random.default_rng(4)
+    for dx, dy in ((1.0, 1.0), (0.8, 1.7)):
+        u, v, h = (np.stack([a * (1.0 + 0.5 * k) for k in range(L)]).astype(dtype)
+                   for a in syn.random_vorticity(W, H, dtype=np.float64))
+        h = (10.0 + (h - 10.0)).astype(dtype)
+        p = (1013.25 + rng.uniform(-5, 5, (L, H, W))).astype(dtype)
+        t = (288.15 + rng.uniform(-3, 3, (L, H, W))).astype(dtype)
+        q = rng.uniform(0.0, 0.02, (L, H, W)).astype(dtype)
+        s = cuda_sim(W, H, 2, integ, "auto", coriolis_f=0.1, dx=dx, dy=dy, dtype=dtype, num_levels=L, extended=EXT)
+        assert s.kernel_name == "stage_direct"
+        s.set_state(u, v, h, p=p, t=t, q=q)
+        s.step(5)
+        got = {n: s.get_field(n) for n in ("u", "h", "p", "t", "q")}
+        s.close()
+        for lev in range(L):
+            o = Oracle(W, H, 2, integ, coriolis_f=0.1, dx=dx, dy=dy, dtype=dtype, extended=EXT)
+            o.set_state(u[lev], v[lev], h[lev], p=p[lev], t=t[lev], q=q[lev])
+            o.step(5)
+            for n in got:
+                assert_bit_equal(got[n][lev], o.get_field(n), f"extended primitive i{integ} d{dx} level {lev} {n}")
+            o.close()
+    with pytest.raises(ValueError, match="not available"):
+        cuda_sim(32, 32, 2, 1, "step_fused_tma", extended=EXT)
+
+
 def test_extended_physics_general_spacing_and_sanity():
     ic = syn.random_vorticity(96, 64)
     # any spacing: AUTO falls back to the per-stage kernel (exact three-operation division), still the oracle's bits
