@@ -64,6 +64,13 @@ WORKLOADS = {
                             extended=(1.0e-5, 0.05, 0.02), classical=True,
                             desc="beta-plane shallow water with viscosity/diffusivity {W}x{H} fp32, textbook RK4 "
                                  "(WSB_PHYSICS_EXTENDED: not in the reference)", bpc_stage=192, bpc_step=24),
+    # NOT a reference configuration: extended physics on the Primitive model (p, T, q transported by the flow), per-stage
+    # kernels; algorithmic bytes per cell-step of RK2: (6 + 9) fields for u, v, h + (8 + 11) for the tracer stages
+    "prim2048x64_ext": dict(W=2048, rows=2048, model="primitive", integ="rk2", dtype="f32", levels=64,
+                            scaling="weak", metric="grid cell-updates/sec (Primitive 64-level RK2 step, extended physics)",
+                            extended=(1.0e-5, 0.05, 0.02),
+                            desc="Primitive {W}x{H}x64 levels fp32 RK2, beta plane + viscosity + tracer transport of "
+                                 "p, T, q (WSB_PHYSICS_EXTENDED: not in the reference)", bpc_stage=136, bpc_step=136),
     "swe32768_rk4": dict(W=32768, rows=32768, model="shallow_water", integ="rk4", dtype="f32", levels=1,
                          scaling="strong", metric="grid cell-updates/sec (RK4 SWE step)",
                          desc="SWE {W}x{H} fp32 RK4 (reference-parity combine), strong scaling",
@@ -478,9 +485,18 @@ def run_b200_arm(args, wl, rank, world, local_rank):
     if not args.no_other_configs and args.workload == "swe8192_rk4":
         if world == 1:
             for name, arith in (("swe8192_euler", "strict"), ("baro16384_f64", "strict"), ("prim2048x64", "strict"),
-                                ("swe8192_rk4_div", "strict"), ("swe8192_rk4", "folded"), ("swe8192_rk4_ext", "strict")):
-                others.append(sub_line(name, arith))
-        strong = sub_line("swe32768_rk4", "strict", steps=max(5, min(args.steps, 10)))
+                                ("swe8192_rk4_div", "strict"), ("swe8192_rk4", "folded"), ("swe8192_rk4_ext", "strict"),
+                                ("prim2048x64_ext", "strict")):
+                try:
+                    others.append(sub_line(name, arith))
+                except Exception as exc:  # a failing sub-line is reported, it does not take the headline with it
+                    others.append({"name": name, "error": repr(exc)})
+        try:
+            strong = sub_line("swe32768_rk4", "strict", steps=max(5, min(args.steps, 10)))
+        except Exception as exc:
+            if world > 1:
+                raise  # collective: every rank would have to fail alike
+            strong = {"name": "swe32768_rk4", "error": repr(exc)}
 
     if rank == 0:
         line = {
