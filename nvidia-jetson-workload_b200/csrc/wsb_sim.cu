@@ -944,6 +944,12 @@ int wsb_grid_set_spacing(wsb_grid *g, double dx, double dy) {
     if (!g) return fail(WSB_ERR_INVALID_ARGUMENT, "grid is NULL");
     if (!(dx > 0.0) || !(dy > 0.0))
         return fail(WSB_ERR_INVALID_ARGUMENT, "Grid spacing must be positive");  // weather_grid.cpp:74-76
+    if (g->owner && g->owner->cfg.physics_mode == WSB_PHYSICS_EXTENDED && g->owner->path == PATH_STEP_TMA) {
+        const double fx = g->dtype == WSB_F32 ? (double)(float)dx : dx, fy = g->dtype == WSB_F32 ? (double)(float)dy : dy;
+        if (!is_pow2(2.0 * fx) || !is_pow2(2.0 * fy))  // that kernel family exists for exact-reciprocal spacing only
+            return fail(WSB_ERR_INVALID_ARGUMENT, "extended physics on the whole-step kernels needs power-of-two spacing; "
+                                                  "create the simulation with kernel_variant STAGE_DIRECT for this spacing");
+    }
     g->dx = g->dtype == WSB_F32 ? (double)(float)dx : dx;
     g->dy = g->dtype == WSB_F32 ? (double)(float)dy : dy;
     set_spacing_derived(g);
@@ -994,7 +1000,10 @@ int wsb_grid_set_field(wsb_grid *g, int32_t field, const void *host, int32_t hos
     g->transfer_ms += ms;
     if (g->owner) {
         g->owner->metrics.memory_transfer_time_ms += ms;
-        if (field <= WSB_FIELD_HEIGHT) g->owner->halo_valid = false;
+        if (field <= WSB_FIELD_HEIGHT) {
+            g->owner->halo_valid = false;
+            g->owner->ghosts_in_flight = false;
+        }
     }
     return WSB_OK;
 }
@@ -1519,6 +1528,7 @@ int wsb_sim_step_host(wsb_sim *s, const void *u, const void *v, const void *h, v
     for (int k = WSB_FIELD_PRESSURE; k <= WSB_FIELD_HUMIDITY; ++k) std::swap(g->f[k], s->alt[k]);
     s->diag_dirty = true;
     s->halo_valid = false;  // the new state's ghost rows have not been exchanged
+    s->ghosts_in_flight = false;
     if (s->dtype == WSB_F32) s->time = (double)((float)s->time + (float)s->dt);
     else s->time += s->dt;
     s->step += 1;

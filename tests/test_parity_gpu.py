@@ -597,6 +597,14 @@ def test_extended_primitive_tracers_vs_its_oracle(integ, dtype):
             o.close()
     with pytest.raises(ValueError, match="not available"):
         cuda_sim(32, 32, 2, 1, "step_fused_tma", extended=EXT)
+    # the whole-step extended kernels exist for exact-reciprocal spacing: a later set_spacing is refused, not mis-run
+    s = cuda_sim(64, 64, 0, 2, "auto", extended=EXT)
+    assert s.kernel_name == "step_fused_tma"
+    with pytest.raises(ValueError, match="power-of-two spacing"):
+        s.grid.set_spacing(0.8, 1.0)
+    s.grid.set_spacing(0.5, 2.0)
+    s.step(1)
+    s.close()
 
 
 def test_extended_physics_general_spacing_and_sanity():
