@@ -277,6 +277,68 @@ __device__ __forceinline__ void tendency_pair(const PhysicsF2 &ph, F2 u, F2 v, F
     dh = f2_sub_prod(f2_sub_prod(f2_mul(u, nhx), f2_mul(h, s)), f2_mul(v, hy));
 }
 
+// ---- packed path for a spacing whose 2dx / 2dy are NOT powers of two ---------------------------------------------
+// tendency_pair with every centred difference divided by the exact three-operation sequence of div_by_invariant,
+// packed: q = D*r, e = D - q*d (one FFMA2 -- an intended fused operation, not a contraction), q' = q + e*r. The x
+// quotients are produced negated (r -> -r: every rounding is sign-symmetric), as tendency_pair wants them. Valid
+// only where every difference is +0 or of ordinary magnitude: the CALLER guarantees that (wsb_step_tma.cu keeps
+// a warp-uniform flag per input row: all cells +0 or 2^-70 <= |x| < 2^99, hence differences +0 or 2^-93 <= |D| <
+// 2^100) and takes the scalar path with the IEEE fallback for any other row.
+struct PhysicsDivF2 {
+    F2 nrx, ry;    // -RN(1/(2dx)), RN(1/(2dy))
+    F2 ddx, nddy;  // 2dx, -(2dy)
+    F2 g, ng, f, nf;
+};
+__device__ __forceinline__ PhysicsDivF2 physics_div_f2(const Physics<float> &ph) {
+    PhysicsDivF2 p;
+    p.nrx = f2_splat(-ph.rdx);
+    p.ry = f2_splat(ph.rdy);
+    p.ddx = f2_splat(ph.ddx);
+    p.nddy = f2_splat(-ph.ddy);
+    p.g = f2_splat(ph.g);
+    p.ng = f2_splat(-ph.g);
+    p.f = f2_splat(ph.f);
+    p.nf = f2_splat(-ph.f);
+    return p;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(r);
+}
+// -(D / d) with nr = -RN(1/d):  nq = D*nr;  e = D + nq*d;  nq' = nq + e*nr
+__device__ __forceinline__ F2 f2_neg_div(F2 D, F2 nr, F2 d) {
+    const F2 nq = f2_mul(D, nr);
+    return f2_fma(f2_fma(nq, d, D), nr, nq);
+}
+// D / d with r = RN(1/d), nd = -d:  q = D*r;  e = D + q*nd;  q' = q + e*r
+__device__ __forceinline__ F2 f2_div(F2 D, F2 r, F2 nd) {
+    const F2 q = f2_mul(D, r);
+    return f2_fma(f2_fma(q, nd, D), r, q);
+}
+__device__ __forceinline__ bool ordinary_input(float x) {  // +0, or 2^-70 <= |x| < 2^99
+    const unsigned b = __float_as_uint(x);
+    return b == 0u || ((b << 1) - (57u << 24)) < (169u << 24);
+}
+__device__ __forceinline__ void tendency_pair_div(const PhysicsDivF2 &ph, F2 u, F2 v, F2 h, float uLft, float uRgt, F2 uU,
+                                                  F2 uD, float vLft, float vRgt, F2 vU, F2 vD, float hLft, float hRgt,
+                                                  F2 hU, F2 hD, F2 &du, F2 &dv, F2 &dh) {
+    const F2 dux = F2{__fsub_rn(u.y, uLft), __fsub_rn(uRgt, u.x)};
+    const F2 dvx = F2{__fsub_rn(v.y, vLft), __fsub_rn(vRgt, v.x)};
+    const F2 dhx = F2{__fsub_rn(h.y, hLft), __fsub_rn(hRgt, h.x)};
+    const F2 nux = f2_neg_div(dux, ph.nrx, ph.ddx);
+    const F2 uy = f2_div(f2_sub_packed(uD, uU), ph.ry, ph.nddy);
+    const F2 nvx = f2_neg_div(dvx, ph.nrx, ph.ddx);
+    const F2 vy = f2_div(f2_sub_packed(vD, vU), ph.ry, ph.nddy);
+    const F2 nhx = f2_neg_div(dhx, ph.nrx, ph.ddx);
+    const F2 hy = f2_div(f2_sub_packed(hD, hU), ph.ry, ph.nddy);
+    // from here on: tendency_pair, operation for operation
+    du = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, nux), f2_mul(v, uy)), f2_mul(ph.ng, nhx)), f2_mul(ph.nf, v));
+    dv = f2_sub_prod(f2_sub_prod(f2_sub_prod(f2_mul(u, nvx), f2_mul(v, vy)), f2_mul(ph.g, hy)), f2_mul(ph.f, u));
+    const F2 s = f2_sub_prod(vy, nux);
+    dh = f2_sub_prod(f2_sub_prod(f2_mul(u, nhx), f2_mul(h, s)), f2_mul(v, hy));
+}
+
 // Extended physics, packed (exact-reciprocal spacing): tendency_pair with the row's Coriolis parameter instead of the
 // constant f, plus nu*lap(u), nu*lap(v), kappa*lap(h). Same operations as tendency_cell_ext<float, true>, bit for bit:
 // (a - 2c) is c2 := (-2)*c subtracted as a product, p*idx2 + q*idy2 is p*idx2 - q*(-idy2), a + nu*L is a - (-nu)*L.

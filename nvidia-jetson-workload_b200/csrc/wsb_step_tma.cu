@@ -175,6 +175,8 @@ struct SweepT {
     PhysicsF2 ph2;    // splatted constants of the packed path
     PhysicsFold phf;  // ... of its folded variant (wsb_arith.cuh)
     PhysicsExtF2 phe; // ... of the extended physics (EXT)
+    PhysicsDivF2 phd; // ... of the packed exact-division path (kPackedDiv)
+    bool div_unproven; // the host has no proven reciprocal for this spacing (ph.rdx == 0): IEEE path everywhere
     float rs;         // FOLD: r = 1/(2dx), folded into every stage coefficient; else unused
     const CUtensorMap *tm_u, *tm_v, *tm_h;  // tiled-TMA descriptors of the y_n planes (kernel parameters)
     int lane, c0, xs;
@@ -193,6 +195,13 @@ struct SweepT {
 
     // packed fp32x2 math (FMUL2/FADD2) is used for the float, 2-cells-per-lane, exact-reciprocal kernels
     static constexpr bool kPacked = std::is_same<T, float>::value && V % 2 == 0 && RECIP;
+    // non-power-of-two spacing: the same packed arithmetic with the exact three-operation division, for rows whose
+    // input cells are all ordinary (tracked per input row in `hz`, see stage()); the scalar path with the IEEE
+    // fallback otherwise
+#ifndef WSB_PACKED_DIV
+#define WSB_PACKED_DIV 1
+#endif
+    static constexpr bool kPackedDiv = WSB_PACKED_DIV != 0 && std::is_same<T, float>::value && V % 2 == 0 && !RECIP && !EXT;
 #ifndef WSB_STEADY_BODY
 #define WSB_STEADY_BODY 1
 #endif
@@ -285,8 +294,9 @@ struct SweepT {
     }
 
     // r: local index of the centre row (EXT: the beta plane needs the global one)
+    // slow (kPackedDiv only, warp-uniform): one of the three input rows holds a cell that is not ordinary
     __device__ __forceinline__ void tendency_row(const Row<T, V> &U, const Row<T, V> &C, const Row<T, V> &D,
-                                                 Row<T, V> &k, int r) const {
+                                                 Row<T, V> &k, int r, bool slow = false) const {
         T fy = T(0);
         if constexpr (EXT) fy = ext_coriolis<T>(ph, r + g.row0);
         T Lft[3], Rgt[3];
@@ -295,7 +305,8 @@ struct SweepT {
             Lft[f] = __shfl_up_sync(kFull, C.f[f][V - 1], 1);
             Rgt[f] = __shfl_down_sync(kFull, C.f[f][0], 1);
         }
-        if constexpr (kPacked) {
+        if constexpr (kPacked || kPackedDiv) {
+            if (!(kPackedDiv && slow)) {
             // pairs of adjacent cells (2p, 2p+1): outer neighbours come from the lane's other cells or the shuffles
 #pragma unroll
             for (int p = 0; p < V / 2; ++p) {
@@ -307,7 +318,10 @@ struct SweepT {
                     rg[f] = (p == V / 2 - 1) ? (float)Rgt[f] : (float)C.f[f][2 * p + 2];
                 }
                 F2 du, dv, dh;
-                if constexpr (EXT)
+                if constexpr (kPackedDiv)
+                    tendency_pair_div(phd, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]), lf[1], rg[1],
+                                      P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
+                else if constexpr (EXT)
                     tendency_pair_ext(ph2, phe, (float)fy, P(C.f[0]), P(C.f[1]), P(C.f[2]), lf[0], rg[0], P(U.f[0]), P(D.f[0]),
                                       lf[1], rg[1], P(U.f[1]), P(D.f[1]), lf[2], rg[2], P(U.f[2]), P(D.f[2]), du, dv, dh);
                 else if constexpr (FOLD)
@@ -321,6 +335,7 @@ struct SweepT {
                 k.f[2][2 * p] = dh.x; k.f[2][2 * p + 1] = dh.y;
             }
             return;
+            }
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -364,6 +379,24 @@ struct SweepT {
         }
     }
 
+    // kPackedDiv: one warp-uniform bit per input row of every stage (group 0: the y rows, group s: the rows stage s
+    // produced; slot = row mod 3) -- set when any lane holds a cell of that row that is not ordinary. A stage takes the
+    // packed division only while the three rows of its input group are clean.
+    __device__ __forceinline__ void mark_row(unsigned &hz, int bit, const Row<T, V> &row) const {
+        if constexpr (kPackedDiv) {
+            bool bad = false;
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int e = 0; e < V; ++e) bad = bad || !ordinary_input((float)row.f[f][e]);
+            const unsigned any = __any_sync(kFull, bad) ? 1u : 0u;
+            hz = (hz & ~(1u << bit)) | (any << bit);
+        }
+    }
+    static __device__ __forceinline__ void copy_mark(unsigned &hz, int from, int to) {
+        if constexpr (kPackedDiv) hz = (hz & ~(1u << to)) | (((hz >> from) & 1u) << to);
+    }
+
     // Steady state of the boundary-free body: every lane is entirely inside or outside the output range (interior
     // strips are never ragged), so the row goes out as three PREDICATED vector stores -- no branch, the loop body
     // stays one basic block.
@@ -384,9 +417,10 @@ struct SweepT {
     // handling is compiled in at all, pipeline-fill iterations just compute on garbage that is never stored.
     // STEADY (PURE only): the pipeline is full and the triple is complete -- no test of any kind in the body.
     template <int PH, int S1, bool PURE, bool STEADY>
-    __device__ __forceinline__ void stage(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool FAST_,
-                                          T *const (&po)[3]) const {
+    __device__ __forceinline__ void stage(Windows &Lv, Row<T, V> (&Yw)[3], unsigned &hz, int n, const Groups &G,
+                                          const bool FAST_, T *const (&po)[3]) const {
         const bool FAST = PURE || FAST_;
+        const bool slow = kPackedDiv && (div_unproven || ((hz >> (3 * (S1 - 1))) & 7u) != 0u);
         constexpr int m3 = (PH - S1 + 12) % 3, m3m = (m3 + 2) % 3, m3p = (m3 + 1) % 3;
         const int r = y0 - NST + n - S1;
         if constexpr (PURE && S1 > 1 && !STEADY) {
@@ -402,6 +436,7 @@ struct SweepT {
                     if (r == gmax) {  // one past the bottom edge: "down" of the last row is the last row
                         asm volatile("");
                         Lv[S1 - 1][m3] = Lv[S1 - 1][m3m];
+                        copy_mark(hz, 3 * S1 + m3m, 3 * S1 + m3);
                     }
                 }
                 return;
@@ -414,17 +449,18 @@ struct SweepT {
         if constexpr (S1 == 1) {
             if constexpr (kYwin) {
                 ld_y<PH, 0>(Yw[PH], G);
+                mark_row(hz, PH, Yw[PH]);
                 yb = Yw[(PH + 2) % 3];
-                tendency_row(Yw[(PH + 1) % 3], yb, Yw[PH], k, r);
+                tendency_row(Yw[(PH + 1) % 3], yb, Yw[PH], k, r, kPackedDiv && (div_unproven || (hz & 7u) != 0u));
             } else {
                 Row<T, V> U, D;
                 ld_y<PH, 2>(U, G);
                 ld_y<PH, 1>(yb, G);
                 ld_y<PH, 0>(D, G);
-                tendency_row(U, yb, D, k, r);
+                tendency_row(U, yb, D, k, r, slow);  // (the y rows are marked in iteration(), also while this stage idles)
             }
         } else {
-            tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k, r);
+            tendency_row(Lv[S1 - 2][m3m], Lv[S1 - 2][m3], Lv[S1 - 2][m3p], k, r, slow);
             if constexpr (kYwin && S1 == 2) yb = Yw[(PH + 1) % 3];
             else ld_y<PH, S1>(yb, G);
         }
@@ -447,11 +483,13 @@ struct SweepT {
 #pragma unroll
                     for (int e = 0; e < V; ++e) t.f[f][e] = axpy<T>(yb.f[f][e], c, k.f[f][e]);
             }
+            if (!FAST && edge_strip) fix_columns(t);
+            mark_row(hz, 3 * S1 + m3, t);
             if (!FAST) {
-                if (edge_strip) fix_columns(t);
                 if (r == gmin) {  // row -1 := row 0 ("up" of the first row)
                     asm volatile("");
                     Lv[S1 - 1][m3m] = t;
+                    copy_mark(hz, 3 * S1 + m3, 3 * S1 + m3m);
                 }
             }
             if constexpr (NST == 4) {
@@ -531,13 +569,18 @@ struct SweepT {
     }
 
     template <int PH, bool PURE, bool STEADY = false>
-    __device__ __forceinline__ void iteration(Windows &Lv, Row<T, V> (&Yw)[3], int n, const Groups &G, const bool fast,
-                                              T *(&po)[3]) const {
-        stage<PH, 1, PURE, STEADY>(Lv, Yw, n, G, fast, po);
-        if constexpr (NST >= 2) stage<PH, 2, PURE, STEADY>(Lv, Yw, n, G, fast, po);
+    __device__ __forceinline__ void iteration(Windows &Lv, Row<T, V> (&Yw)[3], unsigned &hz, int n, const Groups &G,
+                                              const bool fast, T *(&po)[3]) const {
+        if constexpr (kPackedDiv && !PURE) {  // (the boundary-free body marks the row where stage 1 loads it)
+            Row<T, V> yn;
+            ld_y<PH, 0>(yn, G);
+            mark_row(hz, PH, yn);
+        }
+        stage<PH, 1, PURE, STEADY>(Lv, Yw, hz, n, G, fast, po);
+        if constexpr (NST >= 2) stage<PH, 2, PURE, STEADY>(Lv, Yw, hz, n, G, fast, po);
         if constexpr (NST >= 4) {
-            stage<PH, 3, PURE, STEADY>(Lv, Yw, n, G, fast, po);
-            stage<PH, 4, PURE, STEADY>(Lv, Yw, n, G, fast, po);
+            stage<PH, 3, PURE, STEADY>(Lv, Yw, hz, n, G, fast, po);
+            stage<PH, 4, PURE, STEADY>(Lv, Yw, hz, n, G, fast, po);
         }
 #pragma unroll
         for (int f = 0; f < 3; ++f) po[f] += g.pitch;
@@ -554,6 +597,8 @@ struct SweepT {
     __device__ __forceinline__ void run() const {
         Windows Lv;
         Row<T, V> Yw[3];  // y rows n, n-1, n-2 of the boundary-free body
+        // kPackedDiv: every row counts as suspect until it has been looked at
+        unsigned hz = 0xfffu;
         Groups G;
         const T *base = ring + lane * V;
         G.a = base;                            // group 0: rows of triple 0
@@ -578,18 +623,18 @@ struct SweepT {
             if (PURE && kSteadyBody && n > 2 * NST && n + 2 < niter) {
                 // boundary-free body, pipeline full, complete triple: three straight-line iterations (the only
                 // branches left per triple are the mbarrier wait, the producer election and the loop itself)
-                iteration<0, PURE, PURE>(Lv, Yw, n, G, true, po);
+                iteration<0, PURE, PURE>(Lv, Yw, hz, n, G, true, po);
                 refill(q, grp_next);
-                iteration<1, PURE, PURE>(Lv, Yw, n + 1, G, true, po);
-                iteration<2, PURE, PURE>(Lv, Yw, n + 2, G, true, po);
+                iteration<1, PURE, PURE>(Lv, Yw, hz, n + 1, G, true, po);
+                iteration<2, PURE, PURE>(Lv, Yw, hz, n + 2, G, true, po);
             } else {
             // general body: one code path for steady state and boundaries, the boundary tests are skipped by
             // uniform branches in the steady state
-            iteration<0, PURE>(Lv, Yw, n, G, fast, po);
+            iteration<0, PURE>(Lv, Yw, hz, n, G, fast, po);
             refill(q, grp_next);
-            if ((!PURE && fast) || n + 1 < niter) iteration<1, PURE>(Lv, Yw, n + 1, G, fast, po);
+            if ((!PURE && fast) || n + 1 < niter) iteration<1, PURE>(Lv, Yw, hz, n + 1, G, fast, po);
             else { po[0] += g.pitch; po[1] += g.pitch; po[2] += g.pitch; }
-            if ((!PURE && fast) || n + 2 < niter) iteration<2, PURE>(Lv, Yw, n + 2, G, fast, po);
+            if ((!PURE && fast) || n + 2 < niter) iteration<2, PURE>(Lv, Yw, hz, n + 2, G, fast, po);
             }
             if (grp_next == 0) parity ^= 1u;
             grp = grp_next;
@@ -691,6 +736,8 @@ __global__ void __launch_bounds__(32, MINB)
         sw.ph2 = physics_f2(ph);
         sw.phf = physics_fold(ph);
         sw.phe = physics_ext_f2(ph);
+        sw.phd = physics_div_f2(ph);
+        sw.div_unproven = ph.rdx == 0.0f;
         sw.rs = ph.rdx;
     }
     sw.tm_u = &tm_u;
