@@ -288,6 +288,13 @@ WSB_API int wsb_sim_mass_energy(wsb_sim *sim, double *mass, double *energy);
 WSB_API int wsb_sim_time_halo_exchange(wsb_sim *sim, int32_t reps, double *us_per_exchange,
                                        int64_t *bytes_per_neighbour);
 
+/* Introspection (pure host arithmetic, usable without a GPU): the reciprocal the kernels use to divide by a
+ * loop-invariant spacing `divisor` = 2dx or 2dy with the exact three-operation sequence q = x*r; e = x - q*d;
+ * q' = q + e*r (ws.cpp:521-528 divides six times per cell and stage). *reciprocal is RN(1/divisor) if the sequence
+ * is proven to return the correctly rounded quotient for this divisor -- fp32: by exhaustion over all 2^23
+ * significands (about 70 ms, cached per divisor) -- and 0 if the kernels fall back to the IEEE division. */
+WSB_API int wsb_exact_division_reciprocal(double divisor, int32_t dtype, double *reciprocal);
+
 /* ------------------------------------------------- initial conditions -- */
 
 /* The reference's InitialCondition::initialize(grid) family (initial_conditions.cpp:59-535), evaluated

@@ -1625,6 +1625,12 @@ const char *wsb_sim_kernel_name(const wsb_sim *s) {
     }
 }
 
+int wsb_exact_division_reciprocal(double divisor, int32_t dtype, double *reciprocal) {
+    if (!reciprocal || (dtype != WSB_F32 && dtype != WSB_F64)) return fail(WSB_ERR_INVALID_ARGUMENT, "bad argument");
+    *reciprocal = proven_reciprocal(dtype == WSB_F32 ? (double)(float)divisor : divisor, dtype);
+    return WSB_OK;
+}
+
 int wsb_sim_time_halo_exchange(wsb_sim *s, int32_t reps, double *us_per_exchange, int64_t *bytes_per_neighbour) {
     if (!s || !us_per_exchange) return fail(WSB_ERR_INVALID_ARGUMENT, "NULL argument");
     *us_per_exchange = 0.0;

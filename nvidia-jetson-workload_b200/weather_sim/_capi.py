@@ -147,6 +147,7 @@ SIGNATURES = {
     "wsb_sim_kernel_name": (ctypes.c_char_p, [_vp]),
     "wsb_sim_mass_energy": (ctypes.c_int, [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]),
     "wsb_sim_time_halo_exchange": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_dbl), ctypes.POINTER(_i64)]),
+    "wsb_exact_division_reciprocal": (ctypes.c_int, [_dbl, _i32, ctypes.POINTER(_dbl)]),
     "wsb_ic_apply": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_dbl), _i32, ctypes.c_uint32, ctypes.c_char_p]),
     "wsb_ic_fill_host": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_dbl), _i32, ctypes.c_uint32, ctypes.c_char_p,
                                         _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -210,6 +211,14 @@ def nccl_unique_id():
     buf = ctypes.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
     _check(load_library().wsb_nccl_get_unique_id(buf))
     return buf.raw
+
+
+def exact_division_reciprocal(divisor, dtype=np.float32):
+    """RN(1/divisor) if the three-operation division is proven exact for this divisor (fp32: by exhaustion), else 0."""
+    r = ctypes.c_double()
+    _check(load_library().wsb_exact_division_reciprocal(float(divisor), WSB_F64 if np.dtype(dtype) == np.float64 else WSB_F32,
+                                                        ctypes.byref(r)))
+    return r.value
 
 
 def pinned_empty(shape, dtype=np.float32):

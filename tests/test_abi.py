@@ -131,3 +131,21 @@ def test_exact_reciprocal_kernels_contain_no_contracted_fma():
                        text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "check_no_fma: ok" in r.stdout
+
+
+def test_exact_division_reciprocal_is_proven_on_the_host():
+    """Non-power-of-two spacing: the kernels divide by 2dx, 2dy with q = x*r; e = x - q*d; q' = q + e*r. For fp32 the
+    library proves per divisor, by exhaustion over all 2^23 significands, that the sequence returns the IEEE quotient
+    (cached); the same loop is repeated here in numpy for two divisors, on a stride of the significands."""
+    for d in (1.6, 3.4, 1.4, 3.8):
+        r = _capi.exact_division_reciprocal(d)
+        df = np.float32(d)
+        assert r == float(np.float32(1.0) / df) and r != 0.0
+        bits = (np.arange(0, 1 << 23, 37, dtype=np.uint32) | np.uint32(0x3F800000)).view(np.float32)
+        q = bits * np.float32(r)
+        # e = x - q*d exactly (what the FMA computes), in float64: 24-bit x 24-bit products are exact there
+        e = (bits.astype(np.float64) - q.astype(np.float64) * np.float64(df)).astype(np.float32)
+        q1 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(np.float32(r))).astype(np.float32)
+        assert np.array_equal(q1, bits / df)
+    assert _capi.exact_division_reciprocal(3.0e7) == 0.0          # outside the proven window: IEEE division
+    assert _capi.exact_division_reciprocal(1.6, np.float64) == 1.0 / 1.6
