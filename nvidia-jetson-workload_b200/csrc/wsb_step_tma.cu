@@ -899,7 +899,15 @@ cudaError_t launch_impl(const Geometry<T> &g, const Physics<T> &ph, const StepAr
     cfg.numAttrs = (aa.ovl_done && aa.ovl_chain) ? 1 : 0;
     auto launch = [&](auto kernel, size_t smem) {
         cfg.dynamicSmemBytes = smem;
-        return cudaLaunchKernelEx(&cfg, kernel, g, ph, aa, rpc, tu, tv, th);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, g, ph, aa, rpc, tu, tv, th);
+        if (e != cudaSuccess && cfg.numAttrs) {
+            // a context that refuses the programmatic attribute: the same launch, stream-serialised (the chunk-row
+            // counters are satisfied trivially then)
+            cudaGetLastError();
+            cfg.numAttrs = 0;
+            e = cudaLaunchKernelEx(&cfg, kernel, g, ph, aa, rpc, tu, tv, th);
+        }
+        return e;
     };
     if (ph.ext) {
         // extended physics (beta plane, viscosity, diffusivity): power-of-two spacing only on this path (the per-stage
