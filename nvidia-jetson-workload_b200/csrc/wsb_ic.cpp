@@ -403,7 +403,7 @@ int wsb_ic_apply(wsb_grid *grid, const char *name, const double *params, int32_t
     const int nsets = gi.height > block ? 2 : 1;
     float *pin = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr};
-    if (cudaMallocHost((void **)&pin, sizeof(float) * block_floats * 6 * nsets) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&pin, sizeof(float) * block_floats * 6 * nsets, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return wsb::fail(WSB_ERR_OUT_OF_MEMORY, "initial condition: cannot allocate the page-locked staging buffers");
     }
