@@ -245,6 +245,10 @@ int peer_setup(HaloComm *c, void *const local[kPeerPointers], int H, PeerLink *u
     // blobs travel through device staging buffers: [0] mine, [1] from up, [2] from down
     PeerBlob *dev = nullptr;
     WSB_CUDA(cudaMalloc(&dev, 3 * sizeof(PeerBlob)));
+    struct Free {
+        void *p;
+        ~Free() { cudaFree(p); }
+    } free_dev{dev};
     WSB_CUDA(cudaMemsetAsync(dev, 0, 3 * sizeof(PeerBlob), st));
     WSB_CUDA(cudaMemcpyAsync(dev, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
     const int r_up = c->rank - 1, r_dn = c->rank + 1;
@@ -272,7 +276,6 @@ int peer_setup(HaloComm *c, void *const local[kPeerPointers], int H, PeerLink *u
     WSB_CUDA(cudaMemcpyAsync(&agreed, c->scratch, sizeof(agreed), cudaMemcpyDeviceToHost, st));
     WSB_CUDA(cudaMemsetAsync(c->scratch, 0, sizeof(float), st));
     WSB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dev);
     *all_ok = agreed > 0.5f;
     if (!*all_ok) {
         peer_close(up);

@@ -573,17 +573,6 @@ static int enqueue_step_fused(wsb_sim *s, bool chain) {
         s->ghosts_in_flight = true;
         return WSB_OK;
     }
-    static const bool no_exchange = [] {  // timing diagnostics ONLY: results are wrong next to the slab seams
-        const bool v = std::getenv("WSB_DEBUG_NO_EXCHANGE") != nullptr;
-        if (v) std::fprintf(stderr, "[wsb] WSB_DEBUG_NO_EXCHANGE: ghost rows are NOT exchanged -- timing diagnostics only\n");
-        return v;
-    }();
-    if (no_exchange) {
-        a.y_begin = 0; a.y_end = H;
-        WSB_CUDA(launch_step<T>(s, g, ph, a, s->stream));
-        s->metrics.kernel_launches += 1;
-        return WSB_OK;
-    }
     // dependencies captured BEFORE this step re-records the events
     WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_interior, 0));  // previous step's interior rows
     WSB_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_halo, 0));      // ghost rows of the current state

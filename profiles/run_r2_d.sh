@@ -1,6 +1,8 @@
 #!/usr/bin/env bash
 # Round-2 GPU session D (2 GPUs): slab parity incl. multi-level Primitive and the pybind surface, weak-scaling bench
-# with the device-side rendezvous, the bare ghost-exchange timing, and the no-exchange timing diagnostic.
+# with the device-side rendezvous, the bare ghost-exchange timing, and the no-exchange timing diagnostic
+# (WSB_DEBUG_NO_EXCHANGE existed for this session only -- one launch per rank, no ghost exchange, wrong numbers next to
+# the seams, timing only -- and was removed from the library afterwards).
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/r2d_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2d_pytest.log
