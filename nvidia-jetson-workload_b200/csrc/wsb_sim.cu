@@ -299,7 +299,6 @@ struct wsb_sim {
     int rpc = 64;  // rows per chunk of a full-height launch of the TMA whole-step kernel
     unsigned *ovl_err = nullptr;  // mapped host word raised by a CTA whose dependency timed out
     bool ovl_enabled = false;
-    bool ovl_break = false;  // something other than a protocol step was enqueued last
 };
 
 static void *plane_origin(const wsb_sim *s, void *base) {
@@ -644,8 +643,7 @@ static int sim_ensure_halo(wsb_sim *s, bool flag_aware = false) {
 static int sim_enqueue_step(wsb_sim *s, bool follows_step = false) {
     WSB_TRY(sim_ensure_halo(s, s->peer_ok && is_step_path(s->path)));
     if (is_step_path(s->path)) {
-        const bool chain = follows_step && !s->ovl_break && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
-        s->ovl_break = false;
+        const bool chain = follows_step && s->cfg.model != WSB_MODEL_PRIMITIVE_EQUATIONS;
         if (s->dtype == WSB_F64) WSB_TRY(enqueue_step_fused<double>(s, chain));
         else WSB_TRY(enqueue_step_fused<float>(s, chain));
     } else {
