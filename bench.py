@@ -192,14 +192,25 @@ def source_stamp():
 
 
 # ------------------------------------------------------------------------------ reference arm --
-def time_reference_cpu(width, rows, steps, warmup, model=0, integ=2):
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def time_reference_cpu(width, rows, steps, warmup, model=0, integ=2, threads=None):
     """Times the reference's CPU implementation (weather_simulation.cpp:117-158) on a (rows x width) band."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
 
     # torchrun exports OMP_NUM_THREADS=1 to every rank, and libgomp may already be loaded: the team size is set through
     # the OpenMP runtime itself and the number reported is the one the reference's parallel loop really gets
-    want = host_threads()
+    want = threads or host_threads()
     os.environ["OMP_NUM_THREADS"] = str(want)
     cores = (oracle_py.reference_omp_threads(want) if oracle_py.reference_available()
              else oracle_py.oracle_omp_threads(want))
@@ -535,13 +546,18 @@ def run_b200_arm(args, wl, rank, world, local_rank):
                                     "in a step it runs on its own stream beside the interior sweep"}
         if world == 1 and not args.no_cpu_baseline:
             n = min(wl["rows"], 2048 if wl["integ"] != "euler" else 4096)
-            steps = 20 if wl["rows"] >= 2048 else 3
-            r = time_reference_cpu(n, n, steps, 2, MODEL_CODE[wl["model"]], INTEG_CODE[wl["integ"]])
+            # ~10 s of host work at the reference's 25-30 Mcell/s (RK) / 100+ Mcell/s (Euler) with a full OpenMP team
+            steps = (70 if wl["integ"] != "euler" else 60) if wl["rows"] >= 2048 else 3
+            code = (MODEL_CODE[wl["model"]], INTEG_CODE[wl["integ"]])
+            r = time_reference_cpu(n, n, steps, 2, *code)
+            r1 = time_reference_cpu(n, n, max(steps // 14, 2), 1, *code, threads=1)
             line["cpu_baseline"] = {
                 "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                 "sample": f"reference CPU path, {wl['model']} {n}x{n} fp32 {wl['integ']}, {steps} steps after 2 "
                           f"warm-up ({r['seconds']:.1f} s), OpenMP team of {r['cores']} threads (measured); its "
-                          "throughput is flat in grid size (BASELINE.md section 2)"}
+                          "throughput is flat in grid size (BASELINE.md section 2)",
+                "cpu_model": cpu_model(), "host_threads_available": host_threads(),
+                "one_thread_value": r1["value"], "one_thread_seconds": r1["seconds"]}
         emit(line)
     if dist is not None:
         dist.barrier()

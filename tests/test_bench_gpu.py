@@ -34,6 +34,7 @@ def test_bench_line_has_the_contract_keys():
     assert e["value"] < d["value"]  # host copies are inside the timed region
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0
+    assert c["one_thread_value"] > 0 and c["cpu_model"] and c["host_threads_available"] >= c["cores"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "workload" in d["config"] and "model" not in d["config"]
 
