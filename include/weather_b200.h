@@ -101,7 +101,7 @@ typedef enum wsb_physics_mode {
                                   every model and integrator; power-of-two spacing on the whole-step kernels.
                                   On WSB_MODEL_PRIMITIVE_EQUATIONS it also replaces the constant T/p drift by
                                   transport of p, T, q with the level's flow (advection + diffusivity; per-stage
-                                  kernels, one rank). */
+                                  kernels; on row slabs the tracers' ghost rows are exchanged every stage). */
 } wsb_physics_mode;
 
 /* Which hand-written sm_100a path advances the state. All variants produce bit-identical results. */

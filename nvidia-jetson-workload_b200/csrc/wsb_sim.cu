@@ -276,7 +276,7 @@ struct wsb_sim {
     cudaEvent_t ev_up[kMaxSlabs] = {}, ev_done[kMaxSlabs] = {};
     cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_edge = nullptr, ev_halo = nullptr, ev_interior = nullptr;
-    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_align = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_align = nullptr, ev_tracer = nullptr;
     bool run_open = false;    // ev_start recorded, ev_stop pending
     double last_run_ms = 0.0;
     wsb_metrics metrics{};
@@ -443,6 +443,17 @@ static int enqueue_step_stages(wsb_sim *s) {
         s->metrics.kernel_launches += 1;
         return WSB_OK;
     };
+    // Row slabs: a tracer stage reads one ghost row of its input tracers (the stage's velocity ghosts come with the
+    // (u, v, h) exchange of enqueue_stage). Exchanged on the comm stream after everything the main stream has
+    // enqueued so far (the planes' producer, and the last reader of the ghost rows being overwritten); the main
+    // stream waits for it. No overlap is attempted: this model is an HBM-bound opt-in on the per-stage kernels.
+    auto tracer_ghosts = [&](void *const P[3]) -> int {
+        if (!s->comm) return WSB_OK;
+        WSB_CUDA(cudaEventRecord(s->ev_tracer, s->stream));
+        WSB_TRY(sim_exchange(s, P, 1, s->ev_tracer));
+        WSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        return WSB_OK;
+    };
     void *tr_cur[3] = {nullptr, nullptr, nullptr}, *tr_next[3] = {nullptr, nullptr, nullptr};
     if (prim_ext(s)) {
         for (int k = 0; k < 3; ++k) {
@@ -452,6 +463,7 @@ static int enqueue_step_stages(wsb_sim *s) {
             tr_cur[k] = s->cur.f[tf[k]].base;
             tr_next[k] = s->alt[tf[k]].base;
         }
+        WSB_TRY(tracer_ghosts(tr_cur));  // every step: p, T, q may have been set by the user in between
     }
     if (s->nstages == 1) {  // weather_simulation.cpp:160-218
         a.S = Y; a.O = planes<T>(s, s->next); a.c = dt;
@@ -460,7 +472,10 @@ static int enqueue_step_stages(wsb_sim *s) {
     } else if (s->nstages == 2) {  // :220-323
         a.S = Y; a.O = planes<T>(s, s->tA); a.c = half_dt;
         WSB_TRY(enqueue_stage<T>(s, a, s->tA, true));
-        if (prim_ext(s)) WSB_TRY(tracer_stage(Y, tr_cur, s->trA, half_dt));
+        if (prim_ext(s)) {
+            WSB_TRY(tracer_stage(Y, tr_cur, s->trA, half_dt));
+            WSB_TRY(tracer_ghosts(s->trA));
+        }
         a.S = planes<const T>(s, s->tA); a.O = planes<T>(s, s->next); a.c = dt;
         WSB_TRY(enqueue_stage<T>(s, a, s->next, true));
         if (prim_ext(s)) WSB_TRY(tracer_stage(planes<const T>(s, s->tA), s->trA, tr_next, dt));
@@ -1131,7 +1146,8 @@ static void sim_free(wsb_sim *s) {
     if (s->ovl_done) cudaFree(s->ovl_done);
     if (s->ovl_err) cudaFreeHost(s->ovl_err);
     grid_fini(&s->cur);
-    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior, s->ev_align};
+    cudaEvent_t evs[] = {s->ev_start, s->ev_stop, s->ev_edge, s->ev_halo, s->ev_h0, s->ev_h1, s->ev_interior, s->ev_align,
+                         s->ev_tracer};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
@@ -1211,7 +1227,7 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         s->cur.owner = s;
         for (int k = 0; k < WSB_NUM_FIELDS; ++k) s->alt[k].uniform = (double)kResetValue[k];
         cudaEvent_t *evs[] = {&s->ev_start, &s->ev_stop, &s->ev_edge, &s->ev_halo, &s->ev_h0, &s->ev_h1, &s->ev_interior,
-                              &s->ev_align};
+                              &s->ev_align, &s->ev_tracer};
         for (cudaEvent_t *e : evs)
             if (cudaEventCreate(e) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
         if (st != WSB_OK) break;
@@ -1223,10 +1239,6 @@ int wsb_sim_create(const wsb_config *config, wsb_sim **out) {
         const bool ext = c.physics_mode == WSB_PHYSICS_EXTENDED;
         // (the extended Primitive model needs the midpoint velocity in HBM for its tracer stage: per-stage kernels)
         const bool pext = ext && c.model == WSB_MODEL_PRIMITIVE_EQUATIONS;
-        if (pext && c.nranks > 1) {
-            st = fail(WSB_ERR_INVALID_ARGUMENT, "extended physics on the PrimitiveEquations model runs on one rank");
-            break;
-        }
         const bool reg_ok = step_fused_supported(s->nstages, s->dtype) && !classical4 && !ext;
         const bool tma_ok = step_tma_supported(s->nstages, s->dtype) && !pext &&  // incl. the classical RK4 opt-in
                             (!ext || (is_pow2(2.0 * (double)(float)c.dx) && is_pow2(2.0 * (double)(float)c.dy)));

@@ -22,6 +22,46 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _extended_primitive_slabs(rank, world, msgs):
+    """Extended Primitive model on slabs (called inside an initialised gloo group; also by
+    profiles/tools/check_slab_ext_primitive.py): p, T, q are transported, so THEIR ghost rows travel too."""
+    from oracle_py import Oracle
+    from weather_sim import distributed as wd
+    from weather_sim import synthetic as syn
+
+    ext = (0.02, 0.05, 0.03)
+    W, H, Lv = 90, 53, 2
+    rng = np.random.default_rng(4)
+    for integ, dx, dy in ((1, 1.0, 1.0), (0, 0.8, 1.7)):
+        u, v, h = syn.white_noise_state(W, H, seed=33)
+        u3, v3, h3 = (np.stack([a * (1.0 + 0.5 * k) for k in range(Lv)]).astype(np.float32) for a in (u, v, h - 10.0))
+        h3 += 10.0
+        p3 = (1013.25 + rng.uniform(-5, 5, (Lv, H, W))).astype(np.float32)
+        t3 = (288.15 + rng.uniform(-3, 3, (Lv, H, W))).astype(np.float32)
+        q3 = rng.uniform(0.0, 0.02, (Lv, H, W)).astype(np.float32)
+        sim = wd.slab_simulation(W, H, rank, world, device_id=rank, model="primitive", integrator=integ,
+                                 num_levels=Lv, coriolis_f=0.1, dx=dx, dy=dy, max_time=1e30, extended=ext)
+        r0, n = sim.local_rows
+        sim.set_state(*(a[:, r0:r0 + n] for a in (u3, v3, h3)), p=p3[:, r0:r0 + n], t=t3[:, r0:r0 + n],
+                      q=q3[:, r0:r0 + n])
+        sim.step(2)
+        sim.set_state(q=q3[:, r0:r0 + n])  # a field written between steps: its ghost rows must follow
+        sim.step(2)
+        got = {k: wd.gather_rows(sim.get_field(k), 0) for k in ("u", "h", "p", "t", "q")}
+        sim.close()
+        if rank == 0:
+            for lev in range(Lv):
+                o = Oracle(W, H, 2, integ, coriolis_f=0.1, dx=dx, dy=dy, extended=ext)
+                o.set_state(u3[lev], v3[lev], h3[lev], p=p3[lev], t=t3[lev], q=q3[lev])
+                o.step(2)
+                o.set_state(q=q3[lev])
+                o.step(2)
+                for k in got:
+                    if got[k][lev].tobytes() != o.get_field(k).tobytes():
+                        msgs.append(f"extended primitive slabs integ{integ} dx{dx} level {lev} field {k} differs")
+                o.close()
+
+
 def _worker(rank, world, port, cases, out_q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "nvidia-jetson-workload_b200"), os.path.join(ROOT, "oracle")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -142,6 +182,7 @@ def _worker(rank, world, port, cases, out_q):
                 if got[k].tobytes() != o.get_field(k).tobytes():
                     msgs.append(f"extended physics on slabs: field {k} differs")
             o.close()
+        _extended_primitive_slabs(rank, world, msgs)
         # the drop-in surface on slabs: pyweather_sim.SimulationConfig.rank / nranks / nccl_unique_id
         import weather_sim.pyweather_sim as m
         W, H = 120, 90
