@@ -236,6 +236,14 @@ def time_reference_cpu(width, rows, steps, warmup, model=0, integ=2, threads=Non
             "ms_per_step": dt / steps * 1e3}
 
 
+def config1_reference_cpu():
+    """BASELINE config 1 exactly as specified (SWE 256^2 fp32 Euler, 1000 steps) on the reference's CPU path
+    ("CPU baseline timing")."""
+    r = time_reference_cpu(256, 256, 1000, 0, MODEL_CODE["shallow_water"], INTEG_CODE["euler"])
+    return {"value": r["value"], "unit": UNIT, "seconds": r["seconds"], "cores": r["cores"], "kind": r["kind"],
+            "workload": "SWE 256x256 fp32 Euler, 1000 steps (BASELINE config 1)"}
+
+
 def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
@@ -558,6 +566,11 @@ def run_b200_arm(args, wl, rank, world, local_rank):
                           "throughput is flat in grid size (BASELINE.md section 2)",
                 "cpu_model": cpu_model(), "host_threads_available": host_threads(),
                 "one_thread_value": r1["value"], "one_thread_seconds": r1["seconds"]}
+            if args.workload == "swe8192_rk4":
+                try:
+                    line["cpu_baseline"]["config1"] = config1_reference_cpu()
+                except Exception as e:  # a reported extra, never a reason to lose the line
+                    line["cpu_baseline"]["config1"] = {"error": f"{type(e).__name__}: {e}"}
         emit(line)
     if dist is not None:
         dist.barrier()
